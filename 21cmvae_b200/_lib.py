@@ -1,0 +1,286 @@
+"""ctypes binding of the vae21 C-ABI library (include/vae21.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a)
+as ``21cmvae_b200/libvae21.so``.  There is no CPU fallback: if the library
+is missing or no GPU is present, every compute call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+import weakref
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("VAE21_LIB", os.path.join(_HERE, "libvae21.so"))
+
+F32, F64 = 0, 1
+FP32_SIMT, TC_BF16X3, TC_FP16X3 = 0, 1, 2
+PRECISIONS = {"fp32": FP32_SIMT, "fp32_simt": FP32_SIMT, "tc": TC_BF16X3, "bf16x3": TC_BF16X3,
+              "tc_bf16x3": TC_BF16X3, "fp16x3": TC_FP16X3, "tc_fp16x3": TC_FP16X3}
+
+EXPORTS = [
+    "vae21_version", "vae21_last_error", "vae21_device_count", "vae21_create", "vae21_destroy",
+    "vae21_set_model", "vae21_set_norm", "vae21_predict", "vae21_forward_normalised", "vae21_chi2",
+    "vae21_host_alloc", "vae21_host_free", "vae21_host_trim", "vae21_get_info", "vae21_time_predict",
+]
+
+
+class Vae21Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"vae21 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """Load libvae21.so (once).  Raises if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(this package has no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        vp, i32, i64, f32p = C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_float)
+        lib.vae21_version.restype = i32
+        lib.vae21_last_error.restype = C.c_char_p
+        lib.vae21_device_count.argtypes = [C.POINTER(i32)]
+        lib.vae21_create.argtypes = [i32, C.POINTER(vp)]
+        lib.vae21_destroy.argtypes = [vp]
+        lib.vae21_set_model.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)]
+        lib.vae21_set_norm.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32), i32,
+                                       C.c_double, i32, f32p, C.c_float]
+        lib.vae21_predict.argtypes = [vp, vp, i32, i32, i64, vp, i32, i32, vp]
+        lib.vae21_forward_normalised.argtypes = [vp, vp, i32, i64, vp, i32, i32, vp]
+        lib.vae21_chi2.argtypes = [vp, vp, i32, i32, i64, f32p, f32p, vp, i32, C.POINTER(C.c_float),
+                                   C.POINTER(i64), i32, vp]
+        lib.vae21_host_alloc.argtypes = [C.c_size_t]
+        lib.vae21_host_alloc.restype = vp
+        lib.vae21_host_free.argtypes = [vp]
+        lib.vae21_host_free.restype = None
+        lib.vae21_host_trim.restype = None
+        lib.vae21_get_info.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_float), C.POINTER(i32)]
+        lib.vae21_time_predict.argtypes = [vp, vp, i32, i64, vp, i32, i32, C.POINTER(C.c_float)]
+        for name in EXPORTS:
+            fn = getattr(lib, name)
+            if fn.restype is C.c_int and name not in ("vae21_version",):
+                pass
+        _lib = lib
+        return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise Vae21Error(rc, load().vae21_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    rc = load().vae21_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+# ---- pinned host arrays ----------------------------------------------------------------------
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """A fresh numpy array in pinned host memory from the library's caching pool.
+    The block returns to the pool when the array (and every view of it) is garbage collected."""
+    lib = load()
+    dtype = np.dtype(dtype)
+    shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    ptr = lib.vae21_host_alloc(max(nbytes, 1))
+    if not ptr:
+        raise MemoryError(f"pinned allocation of {nbytes} bytes failed: {lib.vae21_last_error().decode()}")
+    buf = (C.c_char * max(nbytes, 1)).from_address(ptr)
+    weakref.finalize(buf, lib.vae21_host_free, ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+    return arr
+
+
+# ---- buffer unwrapping -----------------------------------------------------------------------
+
+
+def _unwrap(obj, want_write=False) -> Tuple[int, bool, Tuple[int, ...], np.dtype, Optional[int], object]:
+    """(pointer, on_device, shape, dtype, device_index, keepalive) for numpy arrays, torch tensors and
+    anything exposing __cuda_array_interface__.  Requires C-contiguity."""
+    if isinstance(obj, np.ndarray):
+        if not obj.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        if want_write and not obj.flags["WRITEABLE"]:
+            raise ValueError("output array must be writeable")
+        return obj.ctypes.data, False, obj.shape, obj.dtype, None, obj
+    cai = getattr(obj, "__cuda_array_interface__", None)
+    if cai is not None:
+        if cai.get("strides") is not None:
+            # accept only C-contiguous strides
+            shape = tuple(cai["shape"])
+            item = np.dtype(cai["typestr"]).itemsize
+            exp = []
+            acc = item
+            for s in reversed(shape):
+                exp.append(acc)
+                acc *= s
+            if tuple(reversed(exp)) != tuple(cai["strides"]):
+                raise ValueError("device array must be C-contiguous")
+        dev = getattr(getattr(obj, "device", None), "index", None)
+        return int(cai["data"][0]), True, tuple(cai["shape"]), np.dtype(cai["typestr"]), dev, obj
+    if hasattr(obj, "__dlpack__") and hasattr(obj, "data_ptr"):  # torch CPU tensor
+        t = obj
+        if not t.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        import torch  # noqa: WPS433
+
+        np_dt = {torch.float32: np.float32, torch.float64: np.float64}.get(t.dtype)
+        if np_dt is None:
+            raise TypeError(f"unsupported tensor dtype {t.dtype}")
+        return t.data_ptr(), t.is_cuda, tuple(t.shape), np.dtype(np_dt), (t.device.index if t.is_cuda else None), t
+    raise TypeError(f"unsupported buffer type {type(obj)!r}")
+
+
+class Handle:
+    """One library handle = one GPU.  Not thread-safe (serialise calls, like Keras predict)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        self._h = C.c_void_p()
+        _check(self._lib.vae21_create(int(device), C.byref(self._h)))
+        self.device = int(device)
+        self.dims: Optional[Tuple[int, ...]] = None
+        self._fin = weakref.finalize(self, self._lib.vae21_destroy, self._h)
+
+    def close(self):
+        self._fin()
+
+    # -- configuration
+    def set_model(self, kernels: Sequence[np.ndarray], biases: Sequence[np.ndarray], relu: Sequence[bool]):
+        n = len(kernels)
+        ks = [np.ascontiguousarray(k, dtype=np.float32) for k in kernels]
+        bs = [np.ascontiguousarray(b, dtype=np.float32) for b in biases]
+        dims = [ks[0].shape[0]] + [k.shape[1] for k in ks]
+        for i, (k, b) in enumerate(zip(ks, bs)):
+            if k.shape != (dims[i], dims[i + 1]) or b.shape != (dims[i + 1],):
+                raise ValueError(f"layer {i}: kernel {k.shape} / bias {b.shape} inconsistent")
+        c_dims = (C.c_int * (n + 1))(*dims)
+        c_k = (C.c_void_p * n)(*[k.ctypes.data for k in ks])
+        c_b = (C.c_void_p * n)(*[b.ctypes.data for b in bs])
+        c_r = (C.c_int * n)(*[1 if r else 0 for r in relu])
+        _check(self._lib.vae21_set_model(self._h, n, c_dims, c_k, c_b, c_r))
+        self.dims = tuple(dims)
+
+    def set_norm(self, par_min, par_max, log_mask, floor_col, fx_floor, sig_mean, sig_std):
+        pmin = np.ascontiguousarray(par_min, dtype=np.float64)
+        pmax = np.ascontiguousarray(par_max, dtype=np.float64)
+        mask = np.ascontiguousarray(log_mask, dtype=np.int32)
+        mu = np.ascontiguousarray(sig_mean, dtype=np.float32)
+        _check(self._lib.vae21_set_norm(
+            self._h, len(pmin), pmin.ctypes.data_as(C.POINTER(C.c_double)), pmax.ctypes.data_as(C.POINTER(C.c_double)),
+            mask.ctypes.data_as(C.POINTER(C.c_int)), int(floor_col), float(fx_floor), len(mu),
+            mu.ctypes.data_as(C.POINTER(C.c_float)), float(sig_std)))
+
+    # -- info
+    def info(self):
+        n, ms, tc = C.c_int64(0), C.c_float(0), C.c_int(0)
+        _check(self._lib.vae21_get_info(self._h, C.byref(n), C.byref(ms), C.byref(tc)))
+        return {"kernel_launches": n.value, "last_kernel_ms": ms.value, "tc_supported": bool(tc.value)}
+
+    # -- compute
+    def _prep_in(self, x, width):
+        ptr, dev, shape, dt, didx, keep = _unwrap(x)
+        if len(shape) != 2 or shape[1] != width:
+            raise ValueError(f"expected shape (n, {width}), got {shape}")
+        if dev and didx is not None and didx != self.device:
+            raise ValueError(f"buffer on cuda:{didx}, handle on cuda:{self.device}")
+        return ptr, dev, shape[0], dt, keep
+
+    def _prep_out(self, out, n, width, device_like=None):
+        if out is None:
+            if device_like is not None:
+                import torch
+
+                out = torch.empty((n, width), dtype=torch.float32, device=device_like) if width else \
+                    torch.empty((n,), dtype=torch.float32, device=device_like)
+            else:
+                out = pinned_empty((n, width) if width else (n,), np.float32)
+        ptr, dev, shape, dt, didx, keep = _unwrap(out, want_write=True)
+        exp = (n, width) if width else (n,)
+        if tuple(shape) != exp or dt != np.float32:
+            raise ValueError(f"output must be float32 with shape {exp}, got {dt} {shape}")
+        return out, ptr, dev
+
+    @staticmethod
+    def _stream_ptr(stream, on_device, keep):
+        if stream is not None:
+            return int(getattr(stream, "cuda_stream", stream))
+        if on_device and hasattr(keep, "is_cuda"):
+            import torch
+
+            return int(torch.cuda.current_stream(keep.device).cuda_stream)
+        return 0
+
+    def predict(self, params, out=None, precision=FP32_SIMT, stream=None):
+        if self.dims is None:
+            raise Vae21Error(2, "model not set")
+        ptr, dev, n, dt, keep = self._prep_in(params, self.dims[0])
+        if dt not in (np.float32, np.float64):
+            raise TypeError(f"params dtype {dt} unsupported (float32/float64)")
+        out, optr, odev = self._prep_out(out, n, self.dims[-1], keep.device if dev and hasattr(keep, "is_cuda") else None)
+        _check(self._lib.vae21_predict(self._h, ptr, F64 if dt == np.float64 else F32, int(dev), n, optr, int(odev),
+                                       int(precision), self._stream_ptr(stream, dev and odev, keep)))
+        return out
+
+    def forward_normalised(self, x, out=None, precision=FP32_SIMT, stream=None):
+        if self.dims is None:
+            raise Vae21Error(2, "model not set")
+        ptr, dev, n, dt, keep = self._prep_in(x, self.dims[0])
+        if dt != np.float32:
+            raise TypeError("normalised input must be float32")
+        out, optr, odev = self._prep_out(out, n, self.dims[-1], keep.device if dev and hasattr(keep, "is_cuda") else None)
+        _check(self._lib.vae21_forward_normalised(self._h, ptr, int(dev), n, optr, int(odev), int(precision),
+                                                  self._stream_ptr(stream, dev and odev, keep)))
+        return out
+
+    def chi2(self, params, obs, inv_sigma, out=None, want_chi2=True, want_best=True, precision=FP32_SIMT, stream=None):
+        """Returns (chi2 array or None, best_val, best_idx)."""
+        if self.dims is None:
+            raise Vae21Error(2, "model not set")
+        ptr, dev, n, dt, keep = self._prep_in(params, self.dims[0])
+        if dt not in (np.float32, np.float64):
+            raise TypeError(f"params dtype {dt} unsupported (float32/float64)")
+        nout = self.dims[-1]
+        obs = np.ascontiguousarray(obs, dtype=np.float32)
+        isg = np.ascontiguousarray(np.broadcast_to(np.asarray(inv_sigma, dtype=np.float32), (nout,)))
+        if obs.shape != (nout,):
+            raise ValueError(f"obs must have shape ({nout},)")
+        optr, odev = None, int(dev)
+        if want_chi2:
+            out, optr, odev = self._prep_out(out, n, 0, keep.device if dev and hasattr(keep, "is_cuda") else None)
+        else:
+            out = None
+        bv, bi = C.c_float(float("nan")), C.c_int64(-1)
+        _check(self._lib.vae21_chi2(
+            self._h, ptr, F64 if dt == np.float64 else F32, int(dev), n, obs.ctypes.data_as(C.POINTER(C.c_float)),
+            isg.ctypes.data_as(C.POINTER(C.c_float)), optr, int(odev), C.byref(bv) if want_best else None,
+            C.byref(bi) if want_best else None, int(precision), self._stream_ptr(stream, dev and bool(odev), keep)))
+        return out, (bv.value if want_best else None), (bi.value if want_best else None)
+
+    def time_predict(self, params_dev, out_dev, precision=FP32_SIMT, iters=10) -> float:
+        ptr, dev, n, dt, keep = self._prep_in(params_dev, self.dims[0])
+        out, optr, odev = self._prep_out(out_dev, n, self.dims[-1])
+        if not (dev and odev):
+            raise ValueError("time_predict needs device-resident buffers")
+        ms = C.c_float(0)
+        _check(self._lib.vae21_time_predict(self._h, ptr, F64 if dt == np.float64 else F32, n, optr, int(precision),
+                                            int(iters), C.byref(ms)))
+        return ms.value

@@ -1,0 +1,242 @@
+// FP32-SIMT fused emulator kernel: parameter transform -> Dense chain -> output transform
+// (or fused chi^2) in ONE launch.  This is the parity path: every product is an fp32 FFMA
+// accumulated in k order, bias/ReLU/de-normalisation follow the reference's rounding order.
+//
+// Reference semantics: VeryAccurateEmulator/emulator.py:401-403, preprocess.py:49-110, :27-46.
+//
+// Layout per CTA (256 threads, 64 rows per tile, persistent over tiles):
+//   activations live in shared memory k-major: act[k][m], row stride LDA = 68 floats, two
+//   ping-pong buffers (even / odd layer inputs);
+//   weights stream from global/L2 through a cp.async ring of [KB][Npad] fp32 stages
+//   (host-packed, zero padded: Kpad % 8 == 0, Npad % 32 == 0);
+//   warp w owns rows 8w..8w+7 of the tile; lane t owns columns t, t+32, ... (TN of them):
+//   per k a thread does 2 broadcast LDS.128 (its 8 rows) + TN conflict-free LDS.32 and
+//   8*TN FFMA.
+#pragma once
+#include "common.cuh"
+
+namespace f32k {
+
+constexpr int MT = 64;        // rows per tile
+constexpr int LDA = MT + 4;   // 68: 16B-aligned rows; 17 x 16B chunks per row => conflict-free STS.128
+constexpr int KB = 8;         // k rows per weight stage
+constexpr int NTHREADS = 256;
+constexpr int MAX_SLOTS = 15; // columns per lane => widest layer 480
+
+struct Layer {
+    int K, Kpad, N, Npad, relu;
+    long long w_off;  // float offset into the packed weight array ([Kpad][Npad] row-major)
+    long long b_off;  // float offset into the packed bias array ([Npad])
+};
+
+struct Model {
+    int n_layers;
+    int buf_rows[2];  // rows (k extent) of the two activation buffers
+    int max_npad;
+    Layer L[VAE21_MAX_LAYERS];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// One Dense layer for one 64-row tile.  `in`/`outbuf` are k-major smem activation buffers.
+template <int TN, int WST>
+__device__ __forceinline__ void run_layer(const Layer& L, bool last, const float* __restrict__ Wg,
+                                          const float* __restrict__ Bg, const float* in, float* outbuf, float* wst,
+                                          int stage_floats, const NormConsts& nc, const LaunchArgs& a, long long row0) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Npad = L.Npad;
+    const float* Wl = Wg + L.w_off;
+    const int nkb = L.Kpad / KB;
+    const int chunks = (KB * Npad) >> 2;  // 16-byte chunks per stage
+
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    auto load_stage = [&](int kb, int slot) {
+        const float* src = Wl + static_cast<long long>(kb) * KB * Npad;
+        float* dst = wst + slot * stage_floats;
+        for (int c = tid; c < chunks; c += NTHREADS) cp_async16(dst + 4 * c, src + 4 * c);
+    };
+
+#pragma unroll
+    for (int s = 0; s < WST - 1; ++s) {
+        if (s < nkb) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kb = 0; kb < nkb; ++kb) {
+        cp_async_wait<WST - 2>();
+        __syncthreads();  // stage kb visible to all; everyone is done with the slot refilled below
+        const int nxt = kb + WST - 1;
+        if (nxt < nkb) load_stage(nxt, nxt % WST);
+        cp_async_commit();
+        const float* ws = wst + (kb % WST) * stage_floats + lane;
+        const float* ap = in + (kb * KB) * LDA + 8 * warp;
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(ap + kk * LDA);
+            const float4 a1 = *reinterpret_cast<const float4*>(ap + kk * LDA + 4);
+            const float* wk = ws + kk * Npad;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const float w = wk[32 * j];
+                acc[0][j] = fmaf(a0.x, w, acc[0][j]);
+                acc[1][j] = fmaf(a0.y, w, acc[1][j]);
+                acc[2][j] = fmaf(a0.z, w, acc[2][j]);
+                acc[3][j] = fmaf(a0.w, w, acc[3][j]);
+                acc[4][j] = fmaf(a1.x, w, acc[4][j]);
+                acc[5][j] = fmaf(a1.y, w, acc[5][j]);
+                acc[6][j] = fmaf(a1.z, w, acc[6][j]);
+                acc[7][j] = fmaf(a1.w, w, acc[7][j]);
+            }
+        }
+    }
+
+    const float* Bl = Bg + L.b_off;
+    if (!last) {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = lane + 32 * j;
+            const float b = __ldg(Bl + n);
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v[i] = __fadd_rn(acc[i][j], b);
+                if (L.relu) v[i] = fmaxf(v[i], 0.f);
+            }
+            float4* dst = reinterpret_cast<float4*>(outbuf + n * LDA + 8 * warp);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    } else {
+        const int N = L.N;
+        const long long rbase = row0 + 8 * warp;
+        if (a.out_mode == OUT_CHI2) {
+            float part[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) part[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int n = lane + 32 * j;
+                if (n < N) {
+                    const float b = __ldg(Bl + n), mu = __ldg(a.mu + n), ob = __ldg(a.obs + n), is = __ldg(a.isig + n);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float v = __fadd_rn(acc[i][j], b);
+                        if (L.relu) v = fmaxf(v, 0.f);
+                        v = __fadd_rn(__fmul_rn(v, nc.sd), mu);
+                        const float r = (v - ob) * is;
+                        part[i] = fmaf(r, r, part[i]);
+                    }
+                }
+            }
+            unsigned long long best = ~0ull;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float s = warp_sum(part[i]);
+                const long long row = rbase + i;
+                if (row < a.n) {
+                    if (a.chi2 && lane == 0) a.chi2[row] = s;
+                    const unsigned long long key = pack_min_key(s, static_cast<unsigned long long>(a.row_base + row));
+                    best = key < best ? key : best;
+                }
+            }
+            if (a.argmin_key && lane == 0 && best != ~0ull) atomicMin(a.argmin_key, best);
+        } else {
+            const bool denorm = (a.out_mode == OUT_PREDICT);
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int n = lane + 32 * j;
+                if (n < N) {
+                    const float b = __ldg(Bl + n);
+                    const float mu = denorm ? __ldg(a.mu + n) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const long long row = rbase + i;
+                        if (row < a.n) {
+                            float v = __fadd_rn(acc[i][j], b);
+                            if (L.relu) v = fmaxf(v, 0.f);
+                            if (denorm) v = __fadd_rn(__fmul_rn(v, nc.sd), mu);  // preprocess.py:44-45
+                            __stcs(a.out + row * N + n, v);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();  // outputs visible; weight ring free for the next layer
+}
+
+template <int WST>
+__global__ void __launch_bounds__(NTHREADS, 1)
+vae21_fp32_kernel(const Model m, const NormConsts nc, const LaunchArgs a, const float* __restrict__ Wg,
+                  const float* __restrict__ Bg) {
+    extern __shared__ __align__(16) float smem[];
+    float* const buf0 = smem;
+    float* const buf1 = buf0 + m.buf_rows[0] * LDA;
+    float* wst = buf1 + m.buf_rows[1] * LDA;
+    const int stage_floats = KB * m.max_npad;
+    const int tid = threadIdx.x;
+    const long long ntiles = (a.n + MT - 1) / MT;
+    const int K0 = m.L[0].K, Kpad0 = m.L[0].Kpad;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long row0 = tile * MT;
+        // ---- prologue: load + transform the tile's parameters into buf[0][k][m] ----
+        for (int e = tid; e < MT * Kpad0; e += NTHREADS) {
+            int r, c;
+            float x = 0.f;
+            if (e < MT * K0) {
+                r = e / K0;
+                c = e - r * K0;
+                const long long row = row0 + r;
+                if (row < a.n) {
+                    const long long g = row * K0 + c;
+                    if (a.in_mode == IN_PARAMS_F64)
+                        x = transform_param(reinterpret_cast<const double*>(a.in)[g], c, nc, false);
+                    else if (a.in_mode == IN_PARAMS_F32)
+                        x = transform_param(static_cast<double>(reinterpret_cast<const float*>(a.in)[g]), c, nc, true);
+                    else
+                        x = reinterpret_cast<const float*>(a.in)[g];
+                }
+            } else {  // zero the k padding rows
+                const int e2 = e - MT * K0;
+                c = K0 + e2 / MT;
+                r = e2 - (c - K0) * MT;
+            }
+            buf0[c * LDA + r] = x;
+        }
+        __syncthreads();
+
+        for (int l = 0; l < m.n_layers; ++l) {
+            const Layer& L = m.L[l];
+            const bool last = (l == m.n_layers - 1);
+            const float* in = (l & 1) ? buf1 : buf0;
+            float* ob = (l & 1) ? buf0 : buf1;
+            const int slots = L.Npad >> 5;
+#define VAE21_CASE(T)                                                                             \
+    case T:                                                                                       \
+        run_layer<T, WST>(L, last, Wg, Bg, in, ob, wst, stage_floats, nc, a, row0);               \
+        break;
+            switch (slots) {
+                VAE21_CASE(1) VAE21_CASE(2) VAE21_CASE(3) VAE21_CASE(4) VAE21_CASE(5)
+                VAE21_CASE(6) VAE21_CASE(7) VAE21_CASE(8) VAE21_CASE(9) VAE21_CASE(10)
+                VAE21_CASE(11) VAE21_CASE(12) VAE21_CASE(13) VAE21_CASE(14) VAE21_CASE(15)
+                default: break;
+            }
+#undef VAE21_CASE
+        }
+    }
+}
+
+}  // namespace f32k

@@ -1,0 +1,142 @@
+/*
+ * vae21.h -- C ABI of the B200-native 21cmVAE emulator-evaluation library.
+ *
+ * The reference (christianhbye/21cmVAE) has no FFI: its seam is the Python
+ * method DirectEmulator.predict.  Everything between
+ *   VeryAccurateEmulator/emulator.py:401  pp.par_transform(params, self.par_train)
+ *   VeryAccurateEmulator/emulator.py:402  self.emulator.predict(transformed_params)
+ *   VeryAccurateEmulator/emulator.py:403  pp.unpreproc(proc_pred, self.signal_train)
+ * becomes ONE call into this library (vae21_predict); the squeeze rule at
+ * emulator.py:404-407 stays in Python.  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = OK, non-zero = VAE21_ERR_*;
+ *     vae21_last_error() returns a thread-local message for the last failure.
+ *   - no exceptions or aborts cross the ABI.
+ *   - the caller owns every buffer it passes; the library owns the opaque
+ *     handle, its device copies of weights/constants and its scratch buffers.
+ *   - one handle per (process, GPU); calls on one handle must be serialised
+ *     by the caller; distinct handles are independent.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with VAE21_ERR_CUDA.
+ */
+#ifndef VAE21_H_
+#define VAE21_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAE21_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define VAE21_OK 0
+#define VAE21_ERR_ARG 1         /* bad argument (null pointer, bad enum, n < 0 ...) */
+#define VAE21_ERR_STATE 2       /* model or normalisation constants not set */
+#define VAE21_ERR_CUDA 3        /* CUDA runtime error (message has the CUDA string) */
+#define VAE21_ERR_UNSUPPORTED 4 /* layer stack does not fit the requested kernel */
+#define VAE21_ERR_NOMEM 5
+
+/* params_dtype */
+#define VAE21_F32 0
+#define VAE21_F64 1
+
+/* precision: which kernel evaluates the Dense chain */
+#define VAE21_FP32_SIMT 0   /* FFMA, fp32 accumulate: parity path (<= 1e-5 of amplitude vs TF CPU) */
+#define VAE21_TC_BF16X3 1   /* tcgen05 kind::f16, 3-pass bf16 hi/lo split, fp32 accumulate in TMEM */
+#define VAE21_TC_FP16X3 2   /* same with fp16 hi/lo split (fp32-class error; inputs must stay < 65504) */
+
+typedef struct vae21_handle vae21_handle;
+
+int vae21_version(void);
+const char* vae21_last_error(void);
+int vae21_device_count(int* count);
+
+/* Handle life cycle.  `device` is a CUDA ordinal. */
+int vae21_create(int device, vae21_handle** out);
+int vae21_destroy(vae21_handle* h);
+
+/*
+ * The Dense stack (replaces the tf.keras.Sequential built at emulator.py:37-47
+ * and loaded at emulator.py:333-337).
+ *   dims[n_layers + 1]     layer widths, dims[0] = number of parameters
+ *   kernels[l]             host pointer, fp32 row-major [dims[l], dims[l+1]] (Keras kernel layout)
+ *   biases[l]              host pointer, fp32 [dims[l+1]]
+ *   relu_flags[l]          1 = ReLU after layer l, 0 = linear
+ * Weights are copied, padded and (for the tensor-core path) split/packed on
+ * upload; the host arrays may be freed afterwards.
+ */
+int vae21_set_model(vae21_handle* h, int n_layers, const int* dims, const float* const* kernels,
+                    const float* const* biases, const int* relu_flags);
+
+/*
+ * Normalisation constants (replace the per-call statistics of
+ * preprocess.py:89-101 and :44-45).
+ *   par_min/par_max[n_par] min/max of the log-transformed training parameters (fp64)
+ *   log_mask[n_par]        1 = take log10 of this column first (columns 0..2 in the reference)
+ *   fx_floor               value substituted for an exact 0 in column `floor_col` (1e-6, column 2)
+ *   sig_mean[n_out]        per-bin training mean;  sig_std: scalar training std
+ */
+int vae21_set_norm(vae21_handle* h, int n_par, const double* par_min, const double* par_max, const int* log_mask,
+                   int floor_col, double fx_floor, int n_out, const float* sig_mean, float sig_std);
+
+/*
+ * DirectEmulator.predict (emulator.py:383-407 minus the squeeze rule).
+ *   params   [n, dims[0]] row-major, fp32 or fp64, host or device memory
+ *   out      [n, dims[last]] row-major fp32, host or device memory
+ *   stream   cudaStream_t used when BOTH buffers are on the device (the call
+ *            is then asynchronous); host buffers use the library's own
+ *            copy/compute pipeline and the call returns when `out` is complete.
+ */
+int vae21_predict(vae21_handle* h, const void* params, int params_dtype, int params_on_device, int64_t n, float* out,
+                  int out_on_device, int precision, void* stream);
+
+/*
+ * emu.emulator.predict(x): the bare Dense stack on already-normalised inputs
+ * (emulator.py:402), output in sigma units (no de-normalisation).
+ */
+int vae21_forward_normalised(vae21_handle* h, const float* x, int x_on_device, int64_t n, float* y, int y_on_device,
+                             int precision, void* stream);
+
+/*
+ * Fused likelihood: chi2[i] = sum_k ((predict(params_i)[k] - obs[k]) * inv_sigma[k])^2
+ * without writing the spectra.  obs / inv_sigma are HOST pointers ([n_out],
+ * copied on each call).  chi2 may be NULL when only the argmin is wanted.
+ * best_val/best_idx (host pointers, may be NULL) receive the minimum over the
+ * n rows and its row index (-1 if every chi2 is NaN).  Not in the reference
+ * (callers do this in numpy on the 451-bin output).
+ */
+int vae21_chi2(vae21_handle* h, const void* params, int params_dtype, int params_on_device, int64_t n,
+               const float* obs, const float* inv_sigma, float* chi2, int chi2_on_device, float* best_val,
+               int64_t* best_idx, int precision, void* stream);
+
+/* Pinned host memory from the library's caching pool (for PCIe-rate copies). */
+void* vae21_host_alloc(size_t bytes);
+void vae21_host_free(void* p);
+void vae21_host_trim(void); /* release cached pinned blocks */
+
+/*
+ * Introspection for benchmarks and tests.
+ *   kernel_launches      number of the library's own kernels launched on this handle so far
+ *   last_kernel_ms       device time of the compute kernels of the last call that used the
+ *                        internal pipeline (CUDA events); <0 if not measured
+ *   tc_supported         1 if the loaded model fits the tensor-core kernel
+ */
+int vae21_get_info(vae21_handle* h, int64_t* kernel_launches, float* last_kernel_ms, int* tc_supported);
+
+/*
+ * Benchmark helper: run the predict kernel `iters` times back to back on
+ * device-resident buffers and return the mean device time per launch in ms,
+ * measured with CUDA events on the launching stream.
+ */
+int vae21_time_predict(vae21_handle* h, const void* params_dev, int params_dtype, int64_t n, float* out_dev,
+                       int precision, int iters, float* ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAE21_H_ */
