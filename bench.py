@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched DirectEmulator.predict, 451 z-bins, 1M-row batch per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16x3|fp16x3|fp32] [--impl reference]
+
+One "step" = one pass of the fused kernel over one batch of `--rows` synthetic parameter vectors
+(default 1,000,000 per GPU: BASELINE.json configs[1]) drawn from the prior ranges, the full
+(rows, 451) float32 result written to HBM.  Prints ONE JSON line (rank 0).
+
+`value`   whole-job signals/s, inputs resident in HBM, CUDA-event time of exactly K steps on the
+          launching stream, max over ranks.
+`e2e`     the same metric through the public API (DirectEmulator.predict on HOST numpy buffers in
+          pinned memory): host->device copy of the parameters and device->host copy of every
+          spectrum inside the timed region.
+`roofline` the dominant (only) kernel against MEASURED_PEAKS.json.
+`cpu_baseline` the oracle port (numpy/torch-CPU restatement of the reference; TensorFlow is absent
+          from this image) timed on this box's host cores on a bounded sample.
+--impl reference : the reference arm -- the CPU port alone, all host threads, rank 0 only.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_SIGNAL = 740_608          # 2 * 370,304 MAC
+EXEC_MAC_PER_SIGNAL_TC = 3 * 375_808   # 3 split passes, K/N padding of the MMA shapes
+BYTES_PER_SIGNAL_F64 = 56 + 1804   # fp64 parameters in, 451 fp32 out
+METRIC = "signals/sec (451 z-bins) @1M batch"
+UNIT = "signals/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                clk, mxc = float(f[0]), float(f[1])
+            except ValueError:
+                continue
+            mx = mxc
+            if t0 - 0.05 <= ts <= t1 + 0.1:
+                sm.append(clk)
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_problem(rows, seed):
+    from oracle import refmath as rm  # synthetic inputs + (rank 0) the cpu_baseline checker
+
+    ks, bs, relu = rm.glorot_chain(rm.DIRECT_DIMS, seed=2022)     # random-init weights of the named architecture
+    mu, sd = rm.synthetic_signal_stats(ks, bs, relu)
+    pmin, pmax = rm.prior_par_stats()
+    params = rm.draw_params(rows, seed=seed)
+    return rm, ks, bs, relu, mu, sd, pmin, pmax, params
+
+
+def make_cpu_port(rm, ks, bs, relu, mu, sd, pmin, pmax, threads, as_written_stats=None):
+    """The oracle port on the host: float32 chain as full-batch SGEMMs (torch CPU, `threads` threads),
+    fp64 parameter transform and fp32 de-normalisation in numpy.  `as_written_stats` =
+    (par_train, signal_train) stand-ins: the per-call statistics recomputation of
+    preprocess.py:89-101 / :44-45 is then executed too, as the reference does on every predict."""
+    import torch
+
+    torch.set_num_threads(threads)
+    Wt = [torch.from_numpy(np.ascontiguousarray(k)) for k in ks]
+    Bt = [torch.from_numpy(np.ascontiguousarray(b)) for b in bs]
+
+    def once(p):
+        if as_written_stats is not None:
+            rm.par_stats(as_written_stats[0])
+            rm.signal_stats(as_written_stats[1])
+        x = torch.from_numpy(rm.par_transform_cached(p, pmin, pmax).astype(np.float32))
+        with torch.no_grad():
+            h = x
+            for W, b, r in zip(Wt, Bt, relu):
+                h = torch.addmm(b, h, W)
+                if r:
+                    h = torch.relu_(h)
+        y = h.numpy()
+        y *= np.float32(sd)
+        y += mu
+        return y
+
+    return once
+
+
+def cpu_port_rate(once, params, seconds_budget=12.0):
+    n = len(params)
+    once(params[: min(n, 4096)])
+    t0 = time.perf_counter()
+    once(params)
+    dt = time.perf_counter() - t0
+    reps = int(max(1, min(20, seconds_budget / max(dt, 1e-3))))
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        once(params)
+        times.append(time.perf_counter() - t0)
+    return n / float(np.median(times)), reps
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = len(os.sched_getaffinity(0))
+    rows = min(args.rows, 131_072)
+    rm, ks, bs, relu, mu, sd, pmin, pmax, params = build_problem(rows, 20220322)
+    rng = np.random.default_rng(1)
+    par_train = rm.draw_params(24_562, seed=99)                     # published training-set shape
+    sig_train = (rng.standard_normal((24_562, 451)) * 50).astype(np.float32)
+    once = make_cpu_port(rm, ks, bs, relu, mu, sd, pmin, pmax, threads, (par_train, sig_train))
+    for _ in range(args.warmup):
+        once(params)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        once(params)
+    wall = time.perf_counter() - t0
+    val = rows * args.steps / wall
+    sample = (f"{rows} of the 1M rows per step; torch-CPU fp32 SGEMM chain (full batch, {threads} threads) + numpy "
+              "transforms incl. the reference's per-call training-set statistics (24562-row stand-in); "
+              "TensorFlow absent from the image, so this is the oracle port, not tf.keras")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "DirectEmulator.predict 7->288->352->288->224->451, 451-bin output",
+                       "rows_per_step": rows, "sampled_from_rows": args.rows},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--rows", type=int, default=1_000_000, help="rows per GPU per step")
+    ap.add_argument("--precision", default=os.environ.get("VAE21_BENCH_PRECISION", "auto"))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    if args.gpus > 1 and "RANK" not in os.environ:
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
+                                   os.environ.get("MASTER_PORT", "29533"), os.path.abspath(__file__)] + sys.argv[1:])
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    emu_mod = importlib.import_module("21cmvae_b200.emulator")
+    pp = importlib.import_module("21cmvae_b200.preprocess")
+    kh = importlib.import_module("21cmvae_b200.keras_h5")
+    L = importlib.import_module("21cmvae_b200._lib")
+
+    rm, ks, bs, relu, mu, sd, pmin, pmax, params = build_problem(args.rows, 20220322 + rank)
+    emu = emu_mod.DirectEmulator(stats=pp.NormStats(pmin, pmax, mu, sd), device=local)
+    emu.emulator = emu_mod.DenseModel(kh.DenseChainWeights(ks, bs, relu, name="emulator"), device=local)
+    h = emu._handle()
+    tc = h.info()["tc_supported"]
+    prec_name = args.precision
+    if prec_name == "auto":
+        prec_name = "bf16x3" if tc else "fp32"
+    prec = L.PRECISIONS[prec_name]
+
+    n = args.rows
+    d_params = torch.from_numpy(params).cuda()
+    d_out = torch.empty((n, 451), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step():
+        h.predict(d_params, out=d_out, precision=prec, stream=stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    # quick in-bench sanity check against the oracle on a few rows (not timed)
+    idx = np.arange(0, n, max(1, n // 64))[:64]
+    want = rm.predict(params[idx], ks, bs, relu, pmin, pmax, mu, sd, squeeze=False)
+    got = d_out[torch.from_numpy(idx).cuda()].cpu().numpy().astype(np.float64)
+    max_mk = float(np.abs(got - want).max())
+    rel = float(np.max(np.abs(got - want) / np.max(np.abs(want), axis=1, keepdims=True)))
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.15)
+    launches0 = h.info()["kernel_launches"]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = h.info()["kernel_launches"] - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms_step = ms / args.steps
+    value = world * n / (ms_step * 1e-3)
+
+    # ---- e2e: public API, host numpy in pinned memory -> numpy result, copies inside the timed region
+    e2e_steps = args.e2e_steps or max(3, min(args.steps, 5))
+    hp = L.pinned_empty((n, 7), np.float64)
+    hp[:] = params
+    host_out = L.pinned_empty((n, 451), np.float32)
+    for _ in range(2):
+        emu.predict(hp, precision=prec_name, out=host_out)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = emu.predict(hp, precision=prec_name, out=host_out)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - w0) / e2e_steps
+    checksum = float(res[:: max(1, n // 1000)].sum())
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = world * n / e2e_s
+
+    if rank == 0:
+        pk = peaks()
+        per_gpu_rate = n / (ms_step * 1e-3)
+        if prec_name == "fp32":
+            # CUDA-core path: neither named roof binds; report against the HBM roof (the other candidate)
+            ach = per_gpu_rate * BYTES_PER_SIGNAL_F64 / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                    "traffic": None, "peak_source": pk["source"],
+                    "note": "FP32-SIMT parity path is FFMA-bound (74.4 TFLOP/s nominal): "
+                            f"{per_gpu_rate * FLOP_PER_SIGNAL / 1e12:.1f} TFLOP/s achieved"}
+        else:
+            ach = per_gpu_rate * FLOP_PER_SIGNAL / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": ach / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " (burst, cuBLAS bf16)",
+                    "frac_executed": per_gpu_rate * 2 * EXEC_MAC_PER_SIGNAL_TC / 1e12 / pk["bf16_tflops"],
+                    "hbm_gbs_achieved": per_gpu_rate * BYTES_PER_SIGNAL_F64 / 1e9,
+                    "note": "achieved = algorithmic 740,608 FLOP/signal; frac_executed counts the 3 split passes "
+                            "and MMA-shape padding actually issued to the tensor pipe"}
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tp):
+            roof["traffic"] = json.load(open(tp)).get(prec_name)
+        cpu = None
+        if not args.no_cpu_baseline:
+            threads = len(os.sched_getaffinity(0))
+            sample_rows = min(n, 131_072)
+            once = make_cpu_port(rm, ks, bs, relu, mu, sd, pmin, pmax, threads)
+            rate, reps = cpu_port_rate(once, params[:sample_rows], 12.0)
+            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"first {sample_rows} rows of the batch, median of {reps} runs; torch-CPU fp32 SGEMM chain "
+                             f"({threads} threads) + numpy transforms with cached statistics (TensorFlow absent)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "bf16x3": "bf16x3 split, f32 accumulate", "fp16x3": "fp16x3 split, f32 accumulate"}[prec_name],
+            "data": "synthetic",
+            "config": {"workload": "DirectEmulator.predict 7->288->352->288->224->451, full 451-bin output to HBM",
+                       "rows_per_gpu": n, "params_dtype": "f64", "precision_path": prec_name,
+                       "weights": "random-init (Glorot), shipped emulator.h5 absent from the reference checkout",
+                       "l2": "working set 1.86 GB/step >> 126 MB L2 (no flush needed)", "parallelism": f"rows sharded x{world}"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * 56, "d2h_bytes_per_step": n * 1804,
+                    "steps": e2e_steps, "checksum": checksum},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "check": {"max_abs_err_mK": max_mk, "max_err_over_amplitude": rel, "rows_checked": int(len(idx))},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

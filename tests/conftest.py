@@ -1,0 +1,53 @@
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REFERENCE = "/root/reference"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+def pkg(name=""):
+    return importlib.import_module("21cmvae_b200" + ("." + name if name else ""))
+
+
+@pytest.fixture(scope="session")
+def rm():
+    from oracle import refmath
+
+    return refmath
+
+
+@pytest.fixture(scope="session")
+def ae_golden():
+    d = np.load(os.path.join(GOLDEN, "ae_chain.npz"))
+    n = sum(1 for k in d.files if k.startswith("k") and k[1:].isdigit())
+    return {"x": d["x"], "y64": d["y64"], "latent64": d["latent64"], "relu": [bool(r) for r in d["relu"]],
+            "kernels": [d[f"k{i}"] for i in range(n)], "biases": [d[f"b{i}"] for i in range(n)]}
+
+
+@pytest.fixture(scope="session")
+def direct_fixture(rm):
+    """DirectEmulator architecture (7->288->352->288->224->451) with seeded Glorot weights and the
+    synthetic normalisation constants of SURVEY.md section 8d (real weights/dataset are absent)."""
+    ks, bs, relu = rm.glorot_chain(rm.DIRECT_DIMS, seed=2022)
+    mu, sd = rm.synthetic_signal_stats(ks, bs, relu)
+    pmin, pmax = rm.prior_par_stats()
+    return {"kernels": ks, "biases": bs, "relu": relu, "mu": mu, "sd": sd, "pmin": pmin, "pmax": pmax}
+
+
+def have_gpu():
+    try:
+        return pkg("_lib").device_count() > 0
+    except Exception:  # noqa: BLE001
+        return False

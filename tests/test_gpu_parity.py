@@ -1,0 +1,261 @@
+"""GPU: parity of the CUDA paths with the CPU oracle, through the C-ABI (ctypes) and the
+reference-API mirror.  Tolerances (BASELINE.json north_star):
+  FP32-SIMT path      <= 1e-5 of the per-signal amplitude vs the float64 arbiter
+  tensor-core paths   <= 0.01 mK rms and <= 0.05 mK max vs the float64 arbiter
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, pkg
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5        # of per-signal amplitude
+TC_RMS_TOL_MK = 0.01   # mK
+TC_MAX_TOL_MK = 0.05   # mK
+
+
+def _direct(direct_fixture, device=0):
+    emu = pkg("emulator")
+    pp = pkg("preprocess")
+    kh = pkg("keras_h5")
+    f = direct_fixture
+    e = emu.DirectEmulator(stats=pp.NormStats(f["pmin"], f["pmax"], f["mu"], f["sd"]), device=device)
+    e.emulator = emu.DenseModel(kh.DenseChainWeights(f["kernels"], f["biases"], f["relu"], name="emulator"), device=device)
+    return e
+
+
+def _oracle(rm, f, params, **kw):
+    return rm.predict(params, f["kernels"], f["biases"], f["relu"], f["pmin"], f["pmax"], f["mu"], f["sd"], **kw)
+
+
+def _rel_err(got, want):
+    amp = np.max(np.abs(want), axis=-1, keepdims=True)
+    return float(np.max(np.abs(got.astype(np.float64) - want) / amp))
+
+
+@pytest.fixture(scope="module")
+def emu_direct(direct_fixture):
+    return _direct(direct_fixture)
+
+
+def tc_or_skip(e):
+    if not e.emulator.handle.info()["tc_supported"]:
+        pytest.skip("tensor-core kernel not available for this stack")
+
+
+# ---- config 1: 1,024 synthetic vectors, seed 1024 ----------------------------------
+def test_fp32_config1_matches_oracle(rm, direct_fixture, emu_direct):
+    params = rm.draw_params(1024, seed=1024)
+    want = _oracle(rm, direct_fixture, params)
+    got = emu_direct.predict(params, precision="fp32")
+    assert got.shape == (1024, 451) and got.dtype == np.float32 and got.flags["C_CONTIGUOUS"]
+    assert _rel_err(got, want) <= FP32_TOL
+    # and within fp32 noise of a float32 numpy evaluation (what TF's arithmetic type gives)
+    want32 = _oracle(rm, direct_fixture, params, dtype=np.float32)
+    assert _rel_err(got, want32.astype(np.float64)) <= FP32_TOL
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3"])
+def test_tc_config1_within_mk_tolerance(rm, direct_fixture, emu_direct, prec):
+    tc_or_skip(emu_direct)
+    params = rm.draw_params(1024, seed=1024)
+    want = _oracle(rm, direct_fixture, params)
+    got = emu_direct.predict(params, precision=prec).astype(np.float64)
+    d = got - want
+    assert np.sqrt(np.mean(d * d, axis=1)).max() <= TC_RMS_TOL_MK
+    assert np.abs(d).max() <= TC_MAX_TOL_MK
+
+
+# ---- reference test_predict (tests/test_emulator.py:55-69) --------------------------------------
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_single_vs_batched_and_squeeze(rm, direct_fixture, emu_direct, prec):
+    if prec != "fp32":
+        tc_or_skip(emu_direct)
+    params = rm.draw_params(10, seed=5)
+    single = emu_direct.predict(params[0], precision=prec)
+    assert single.shape == (451,)
+    assert emu_direct.predict(list(params[0]), precision=prec).shape == (451,)      # 1-D list input
+    assert emu_direct.predict(params[:1], precision=prec).shape == (451,)           # (1, 7) squeezes too
+    batched = emu_direct.predict(params, precision=prec)
+    assert batched.shape == (10, 451)
+    assert np.allclose(batched[0], single, atol=5e-5)
+
+
+# ---- ragged sizes, empty input, fx == 0, float32 input -----------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 2, 63, 64, 65, 127, 128, 129, 300, 4097])
+def test_fp32_ragged_sizes(rm, direct_fixture, emu_direct, n):
+    params = rm.draw_params(n, seed=100 + n, zero_fx_frac=0.2).reshape(n, 7)
+    h = emu_direct._handle()
+    got = h.predict(np.ascontiguousarray(params), precision=0)
+    assert got.shape == (n, 451)
+    if n:
+        want = _oracle(rm, direct_fixture, params, squeeze=False)
+        assert _rel_err(got, want) <= FP32_TOL
+
+
+@pytest.mark.parametrize("n", [1, 127, 129, 1000])
+def test_tc_ragged_sizes(rm, direct_fixture, emu_direct, n):
+    tc_or_skip(emu_direct)
+    params = rm.draw_params(n, seed=200 + n, zero_fx_frac=0.2)
+    got = emu_direct._handle().predict(params, precision=1).astype(np.float64)
+    d = got - _oracle(rm, direct_fixture, params, squeeze=False)
+    assert np.sqrt(np.mean(d * d, axis=1)).max() <= TC_RMS_TOL_MK and np.abs(d).max() <= TC_MAX_TOL_MK
+
+
+def test_fx_zero_uses_floor_and_inputs_unmodified(rm, direct_fixture, emu_direct):
+    p = rm.draw_params(64, seed=7, zero_fx_frac=0.0)
+    p[::2, 2] = 0.0
+    keep = p.copy()
+    got = emu_direct.predict(p)
+    assert np.array_equal(p, keep)
+    q = p.copy()
+    q[::2, 2] = 1e-6
+    assert np.array_equal(got, emu_direct.predict(q))  # bit-identical to passing the floor explicitly
+    assert np.all(np.isfinite(got))
+
+
+def test_float32_params_follow_numpy_float32_semantics(rm, direct_fixture, emu_direct):
+    p32 = rm.draw_params(257, seed=12, zero_fx_frac=0.05).astype(np.float32)
+    got = emu_direct.predict(p32)
+    want = _oracle(rm, direct_fixture, p32)  # oracle takes log10 in float32 like numpy does
+    assert _rel_err(got, want) <= FP32_TOL
+
+
+def test_nonpositive_parameters_propagate_nan_like_numpy(rm, direct_fixture, emu_direct):
+    p = rm.draw_params(4, seed=1)
+    p[1, 0] = -1.0  # log10 of a negative number: numpy gives nan, no validation in the reference
+    got = emu_direct.predict(p)
+    assert np.all(np.isnan(got[1])) and np.all(np.isfinite(got[[0, 2, 3]]))
+
+
+# ---- real trained weights: AE emulator + decoder chain (8 layers, 9-wide bottleneck) ------------
+def test_ae_chain_forward_matches_float64_kats(ae_golden):
+    emu = pkg("emulator")
+    kh = pkg("keras_h5")
+    g = ae_golden
+    m = emu.DenseModel(kh.DenseChainWeights(g["kernels"], g["biases"], g["relu"], name="ae_chain"))
+    y = m.predict(g["x"], precision="fp32")
+    assert y.shape == g["y64"].shape
+    assert _rel_err(y, g["y64"]) <= FP32_TOL
+    # hand-recorded KAT of SURVEY.md 8c
+    assert abs(float(y[0].astype(np.float64).sum()) - 9.912912209957) < 2e-3 and int(y[0].argmin()) == 89
+
+
+def test_ae_chain_tc_if_supported(ae_golden):
+    emu = pkg("emulator")
+    kh = pkg("keras_h5")
+    g = ae_golden
+    m = emu.DenseModel(kh.DenseChainWeights(g["kernels"], g["biases"], g["relu"], name="ae_chain"))
+    if not m.handle.info()["tc_supported"]:
+        pytest.skip("AE chain does not fit the tensor-core plan")
+    y = m.predict(g["x"], precision="bf16x3").astype(np.float64)
+    # sigma units; 50 mK per sigma => 0.01 mK rms = 2e-4 sigma, 0.05 mK max = 1e-3 sigma
+    d = y - g["y64"]
+    assert np.sqrt(np.mean(d * d, axis=1)).max() <= 2e-4 and np.abs(d).max() <= 1e-3
+
+
+def test_load_model_end_to_end_from_h5(rm):
+    emu = pkg("emulator")
+    pp = pkg("preprocess")
+    kh = pkg("keras_h5")
+    w = kh.load_dense_chain(os.path.join(GOLDEN, "tiny_keras.h5"))
+    pmin, pmax = rm.prior_par_stats()
+    mu = np.linspace(-100, 0, 11).astype(np.float32)
+    e = emu.DirectEmulator(stats=pp.NormStats(pmin, pmax, mu, np.float32(30)))
+    e.load_model(os.path.join(GOLDEN, "tiny_keras.h5"))
+    p = rm.draw_params(77, seed=4)
+    want = rm.predict(p, w.kernels, w.biases, w.relu, pmin, pmax, mu, np.float32(30))
+    assert _rel_err(e.predict(p), want) <= FP32_TOL
+
+
+# ---- emu.emulator.predict (bare stack on normalised inputs) -------------------------------------
+def test_forward_normalised(rm, direct_fixture, emu_direct):
+    f = direct_fixture
+    x = np.random.default_rng(3).uniform(-1, 1, size=(200, 7)).astype(np.float32)
+    y = emu_direct.emulator.predict(x)
+    want = rm.dense_chain(x, f["kernels"], f["biases"], f["relu"])
+    assert y.shape == (200, 451) and _rel_err(y, want) <= FP32_TOL
+
+
+# ---- fused chi^2 and argmin ----------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_fused_chi2_and_argmin(rm, direct_fixture, emu_direct, prec):
+    if prec != "fp32":
+        tc_or_skip(emu_direct)
+    params = rm.draw_params(5000, seed=77)
+    pred = _oracle(rm, direct_fixture, params)
+    rng = np.random.default_rng(7)
+    truth = pred[1234] + rng.normal(size=451) * 0.5
+    sigma = np.full(451, 25.0)
+    want = rm.chi2(pred, truth.astype(np.float32), (1 / sigma).astype(np.float32))
+    c, bv, bi = emu_direct.chi2(params, truth, sigma, precision=prec, return_argmin=True)
+    assert c.shape == (5000,) and c.dtype == np.float32
+    assert np.allclose(c, want, rtol=2e-4, atol=1e-6)
+    assert bi == int(np.argmin(want)) == 1234 and np.isclose(bv, want[1234], rtol=2e-4)
+    # argmin only (no chi2 array written)
+    h = emu_direct._handle()
+    none, bv2, bi2 = h.chi2(params, truth.astype(np.float32), (1 / sigma).astype(np.float32), want_chi2=False,
+                            precision=pkg("_lib").PRECISIONS[prec])
+    assert none is None and bi2 == 1234 and bv2 == bv
+
+
+# ---- device-resident buffers (torch / __cuda_array_interface__), async on the caller's stream ----
+def test_device_resident_predict(rm, direct_fixture, emu_direct):
+    import torch
+
+    params = rm.draw_params(3000, seed=9)
+    host = emu_direct.predict(params)
+    t = torch.from_numpy(params).cuda()
+    out = emu_direct.predict(t)
+    assert isinstance(out, torch.Tensor) and out.is_cuda and out.shape == (3000, 451)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), host)  # same kernel, same bits
+    pre = torch.empty((3000, 451), dtype=torch.float32, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        emu_direct.predict(t, out=pre)
+    s.synchronize()
+    assert np.array_equal(pre.cpu().numpy(), host)
+
+
+# ---- full BASELINE size: 1M rows, size-independent properties ------------------------------------
+def test_one_million_rows_properties(rm, direct_fixture, emu_direct):
+    import torch
+
+    n = 1_000_000
+    params = rm.draw_params(n, seed=20220322)
+    t = torch.from_numpy(params).cuda()
+    out = torch.empty((n, 451), dtype=torch.float32, device="cuda")
+    emu_direct.predict(t, out=out, precision="fp32")
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out).all())
+    # (1) batch-split invariance: any sub-batch evaluated alone gives the same bits (rows are independent)
+    for lo, hi in [(0, 1000), (499_937, 500_321), (n - 77, n)]:
+        sub = emu_direct.predict(np.ascontiguousarray(params[lo:hi]), precision="fp32")
+        assert np.array_equal(sub, out[lo:hi].cpu().numpy())
+    # (2) spot rows against the oracle
+    idx = np.random.default_rng(0).choice(n, 512, replace=False)
+    want = _oracle(rm, direct_fixture, params[idx])
+    assert _rel_err(out[torch.from_numpy(idx).cuda()].cpu().numpy(), want) <= FP32_TOL
+    # (3) host-buffer pipeline (chunked copies) == device-resident launch, checksum of checksums
+    host = emu_direct.predict(params[:200_000], precision="fp32")
+    assert np.array_equal(host, out[:200_000].cpu().numpy())
+    # (4) tensor-core path on the same million rows stays inside the mK tolerance on sampled rows
+    if emu_direct.emulator.handle.info()["tc_supported"]:
+        out_tc = torch.empty_like(out)
+        emu_direct.predict(t, out=out_tc, precision="bf16x3")
+        torch.cuda.synchronize()
+        d = out_tc[torch.from_numpy(idx).cuda()].cpu().numpy().astype(np.float64) - want
+        assert np.sqrt(np.mean(d * d, axis=1)).max() <= TC_RMS_TOL_MK and np.abs(d).max() <= TC_MAX_TOL_MK
+        dd = (out_tc - out).abs().max().item()
+        assert dd <= TC_MAX_TOL_MK
+
+
+def test_kernel_launch_counter_moves(emu_direct, rm):
+    h = emu_direct._handle()
+    before = h.info()["kernel_launches"]
+    emu_direct.predict(rm.draw_params(10, 1))
+    assert h.info()["kernel_launches"] == before + 1

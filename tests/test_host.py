@@ -1,0 +1,193 @@
+"""CPU: host logic of the reference-API mirror, the Keras-HDF5 loader and the C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, REFERENCE, ROOT, pkg
+
+
+# ---- C ABI -----------------------------------------------------------------------------------
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "vae21.h")).read()
+    declared = set(re.findall(r"\b(vae21_[a-z0-9_]+)\s*\(", hdr))
+    assert {"vae21_predict", "vae21_chi2", "vae21_set_model", "vae21_set_norm", "vae21_forward_normalised"} <= declared
+    L = pkg("_lib")
+    lib = L.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/vae21.h but not exported"
+    assert declared == set(L.EXPORTS)
+    assert lib.vae21_version() == 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    L = pkg("_lib")
+    if L.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(L.Vae21Error):
+        L.Handle(0)
+    emu = pkg("emulator")
+    pp = pkg("preprocess")
+    e = emu.DirectEmulator(stats=pp.NormStats(np.zeros(7), np.ones(7), np.zeros(451, np.float32), np.float32(1)))
+    with pytest.raises(L.Vae21Error):  # fails loudly, never computes on the CPU
+        e.predict(np.ones(7))
+
+
+def test_null_and_state_errors_are_reported_not_crashes():
+    L = pkg("_lib")
+    lib = L.load()
+    assert lib.vae21_create(0, None) == 1  # VAE21_ERR_ARG
+    assert b"null" in lib.vae21_last_error()
+    assert lib.vae21_predict(None, None, 0, 0, 0, None, 0, 0, None) != 0
+    assert lib.vae21_destroy(None) == 0
+
+
+# ---- Keras HDF5 ------------------------------------------------------------------------------
+def test_tiny_keras_file_loads():
+    kh = pkg("keras_h5")
+    w = kh.load_dense_chain(os.path.join(GOLDEN, "tiny_keras.h5"))
+    exp = np.load(os.path.join(GOLDEN, "tiny_keras_expected.npz"))
+    assert w.dims == [7, 16, 24, 11] and w.relu == [True, True, False]
+    assert w.layer_names == ["em_hidden_layer_0", "em_hidden_layer_1", "dense_16"]
+    for i in range(3):
+        assert np.array_equal(w.kernels[i], exp[f"k{i}"]) and np.array_equal(w.biases[i], exp[f"b{i}"])
+
+
+def test_save_load_roundtrip(tmp_path, rm):
+    kh = pkg("keras_h5")
+    ks, bs, relu = rm.glorot_chain(rm.DIRECT_DIMS, seed=4)
+    p = str(tmp_path / "m.h5")
+    kh.save_dense_chain(p, kh.DenseChainWeights(ks, bs, relu, name="emulator"))
+    w = kh.load_dense_chain(p)
+    assert w.dims == list(rm.DIRECT_DIMS) and w.n_params() == 371907  # notebooks/sample_notebook.ipynb:68
+    assert all(np.array_equal(a, b) for a, b in zip(w.kernels, ks))
+    assert all(np.array_equal(a, b) for a, b in zip(w.biases, bs))
+
+
+def test_invalid_model_path_raises_ioerror(tmp_path):
+    kh = pkg("keras_h5")
+    with pytest.raises(IOError):
+        kh.load_dense_chain(str(tmp_path / "missing.h5"))
+    bad = tmp_path / "bad.h5"
+    bad.write_bytes(b"not an hdf5 file at all")
+    with pytest.raises(IOError):
+        kh.load_dense_chain(str(bad))
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present")
+def test_reads_the_shipped_reference_models(ae_golden):
+    kh = pkg("keras_h5")
+    base = REFERENCE + "/VeryAccurateEmulator/models/autoencoder_based_emulator/"
+    em = kh.load_dense_chain(base + "ae_emulator.h5")
+    de = kh.load_dense_chain(base + "decoder.h5")
+    assert em.dims == [7, 352, 352, 352, 224, 9] and de.dims == [9, 32, 352, 451]
+    assert em.n_params() == 332425  # notebooks/sample_notebook.ipynb:423
+    ch = em.concat(de)
+    assert all(np.array_equal(a, b) for a, b in zip(ch.kernels, ae_golden["kernels"]))
+    enc = kh.load_dense_chain(base + "encoder.h5")
+    assert enc.dims == [451, 352, 9]
+    ae = kh.load_dense_chain(base + "autoencoder.h5")
+    assert ae.dims == [451, 352, 9, 32, 352, 451] and ae.n_params() == 333420
+
+
+# ---- reference-API mirror (tests/test_emulator.py, tests/test_preprocess.py of the reference) ----
+def test_gen_model():
+    emu = pkg("emulator")
+    hidden = [32, 64, 256]
+    model = emu._gen_model(7, hidden, 451, "relu")
+    all_dims = hidden + [451]
+    assert len(model.layers) == len(all_dims)
+    for i, layer in enumerate(model.layers):
+        assert layer.output_shape[-1] == all_dims[i]
+    assert emu._gen_model(7, emu.hidden_dims, 451, "relu").count_params() == 371907
+
+
+def test_z_nu():
+    emu = pkg("emulator")
+    assert np.isclose(30, emu.freq2redshift(emu.redshift2freq(30)))
+    nu = emu.redshift2freq(emu.redshifts)
+    assert np.isclose(nu[0], 1420.4057517667 / 6) and np.isclose(nu[-1], 1420.4057517667 / 51)
+    keep = nu.copy()
+    emu.freq2redshift(nu)
+    assert np.array_equal(nu, keep)  # no in-place mutation
+
+
+def test_error_metric(rm):
+    emu = pkg("emulator")
+    rng = np.random.default_rng(0)
+    s = rng.normal(size=(12, 451)) * 50
+    assert np.allclose(emu.error(s, s), 0)
+    t = s + rng.normal(size=s.shape)
+    nu = emu.redshift2freq(emu.redshifts)
+    for kw in [{}, {"relative": False}, {"flow": 50, "fhigh": 100}, {"flow": 50}, {"fhigh": 100, "relative": False}]:
+        a = emu.error(s, t, nu_arr=nu, **kw)
+        b = rm.error(s, t, nu_arr=nu, **kw)
+        assert a.shape == b.shape and np.allclose(a, b)
+    with pytest.raises(ValueError):
+        emu.error(s, t, flow=50)
+
+
+def test_relative_mse_loss():
+    emu = pkg("emulator")
+    pp = pkg("preprocess")
+    rng = np.random.default_rng(1)
+    st = (rng.normal(size=(40, 451)) * 30).astype(np.float32)
+    y_true = pp.preproc(st[:10], st)
+    y_pred = pp.preproc(st[-10:], st)
+    mse = np.mean((y_true - y_pred) ** 2, axis=1)
+    amp = np.max(np.abs(st[:10] / np.std(st)), axis=1)
+    assert np.allclose(emu.relative_mse_loss(st)(y_true, y_pred), mse / amp**2, rtol=1e-5)
+
+
+def test_preprocess_mirror_matches_reference_outputs():
+    pp = pkg("preprocess")
+    d = np.load(os.path.join(GOLDEN, "preprocess.npz"))
+    assert np.array_equal(pp.par_transform(d["params64"], d["par_train"]), d["pt64"])
+    assert np.array_equal(pp.par_transform(d["params32"], d["par_train"]), d["pt32"])
+    assert np.array_equal(pp.par_transform(d["params64"][0], d["par_train"]), d["pt_single"])
+    assert np.array_equal(pp.preproc(d["sig"], d["sig_train"]), d["pre"])
+    assert np.array_equal(pp.unpreproc(d["sig"], d["sig_train"]), d["unpre"])
+    st = pp.NormStats.from_training_set(d["par_train"], d["sig_train"])
+    assert np.array_equal(pp.par_transform_stats(d["params64"], st), d["pt64"])
+    keep = d["params64"].copy()
+    pp.par_transform(d["params64"], d["par_train"])
+    assert np.array_equal(keep, d["params64"])  # inputs are never mutated
+    # tests/test_preprocess.py:12-26 of the reference
+    t = pp.par_transform(d["par_train"], d["par_train"])
+    assert np.allclose(t.min(axis=0), -1) and np.allclose(t.max(axis=0), 1)
+    pre = pp.preproc(d["sig_train"], d["sig_train"])
+    assert np.allclose(pre.mean(axis=0), 0, atol=1e-3)
+    assert np.allclose(pp.unpreproc(pre, d["sig_train"]), d["sig_train"], atol=5e-5)
+
+
+def test_direct_emulator_construction_contract(rm):
+    emu = pkg("emulator")
+    with pytest.raises(IOError):
+        emu.DirectEmulator()  # no dataset anywhere, nothing is downloaded
+    par = rm.draw_params(50, 1)
+    sig = np.random.default_rng(2).normal(size=(50, 451)).astype(np.float32)
+    e = emu.DirectEmulator(par_train=par, signal_train=sig)
+    assert e.par_labels == ["fstar", "Vc", "fx", "tau", "alpha", "nu_min", "Rmfp"]
+    assert e.emulator.input_dim == 7 and e.emulator.output_dim == 451
+    assert [l.units for l in e.emulator.layers] == [288, 352, 288, 224, 451]
+    assert np.allclose(e.frequencies, emu.redshift2freq(e.redshifts))
+    with pytest.raises(NotImplementedError):
+        e.save()
+    with pytest.raises(IOError):
+        e.load_model("/nonexistent/emulator.h5")
+    e2 = emu.DirectEmulator(par_train=par, signal_train=sig, redshifts=None, frequencies=np.array([50.0, 100.0]))
+    assert np.allclose(e2.redshifts, emu.NU_0 / (np.array([50.0, 100.0]) * 1e6) - 1)
+    lines = []
+    e.emulator.summary(print_fn=lines.append)
+    assert any("371,907" in ln for ln in lines)
+
+
+def test_load_model_takes_architecture_from_file(rm):
+    emu = pkg("emulator")
+    pp = pkg("preprocess")
+    e = emu.DirectEmulator(stats=pp.NormStats(np.zeros(7), np.ones(7), np.zeros(11, np.float32), np.float32(1)))
+    e.load_model(os.path.join(GOLDEN, "tiny_keras.h5"))
+    assert [l.units for l in e.emulator.layers] == [16, 24, 11]
+    assert len(e.emulator.get_weights()) == 6

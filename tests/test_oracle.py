@@ -1,0 +1,74 @@
+"""CPU: the oracle against the golden vectors and (when present) the reference's real preprocess.py."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, REFERENCE
+
+
+def test_dense_chain_matches_kats_from_shipped_weights(rm, ae_golden):
+    """float64 known answers derived from the reference's shipped ae_emulator.h5 + decoder.h5."""
+    g = ae_golden
+    y = rm.dense_chain(g["x"], g["kernels"], g["biases"], g["relu"], dtype=np.float64)
+    np.testing.assert_allclose(y, g["y64"], rtol=0, atol=1e-12)
+    # the hand-recorded values of SURVEY.md section 8c (x = 0 and x = linspace(-1, 1, 7))
+    assert np.isclose(y[0].sum(), 9.912912209957, atol=1e-9)
+    assert np.isclose(y[0].min(), -1.262461963071, atol=1e-10) and int(y[0].argmin()) == 89
+    assert np.isclose(y[1].sum(), 194.121759641061, atol=2e-6)  # linspace rounded to float32 first
+    lat = rm.dense_chain(g["x"], g["kernels"][:5], g["biases"][:5], g["relu"][:5])
+    np.testing.assert_allclose(lat, g["latent64"], rtol=0, atol=1e-12)
+    assert np.allclose(lat[0, :3], [-2.08318427071, -1.829909441506, 1.592364183387], atol=1e-9)
+
+
+def test_fp32_chain_within_fp32_budget(rm, ae_golden):
+    g = ae_golden
+    y32 = rm.dense_chain(g["x"], g["kernels"], g["biases"], g["relu"], dtype=np.float32)
+    amp = np.max(np.abs(g["y64"]), axis=1, keepdims=True)
+    assert np.max(np.abs(y32 - g["y64"]) / amp) < 1e-5
+
+
+def test_transforms_match_reference_outputs(rm):
+    """Outputs stored from the reference's own preprocess.py (tests/golden/make_golden.py)."""
+    d = np.load(os.path.join(GOLDEN, "preprocess.npz"))
+    assert np.array_equal(rm.par_transform(d["params64"], d["par_train"]), d["pt64"])
+    assert np.array_equal(rm.par_transform(d["params32"], d["par_train"]), d["pt32"])
+    assert np.array_equal(rm.par_transform(d["params64"][0], d["par_train"]), d["pt_single"])
+    un = rm.unpreproc(d["sig"], d["sig_train"])
+    assert un.dtype == np.float32 and np.array_equal(un, d["unpre"])
+    assert np.array_equal(rm.unpreproc(d["sig"].astype(np.float64), d["sig_train"]), d["unpre64"])
+    # cached-statistics form == per-call form
+    pmin, pmax = rm.par_stats(d["par_train"])
+    assert np.array_equal(rm.par_transform_cached(d["params64"], pmin, pmax), d["pt64"])
+    mu, sd = rm.signal_stats(d["sig_train"])
+    assert np.array_equal(rm.unpreproc_cached(d["sig"], mu, sd), d["unpre"])
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present")
+def test_transforms_match_live_reference(rm):
+    spec = importlib.util.spec_from_file_location("ref_pp", REFERENCE + "/VeryAccurateEmulator/preprocess.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    par_train = rm.draw_params(300, seed=1)
+    p = rm.draw_params(50, seed=2, zero_fx_frac=0.2)
+    assert np.array_equal(ref.par_transform(p, par_train), rm.par_transform(p, par_train))
+    # training parameters map onto [-1, 1] exactly (tests/test_preprocess.py:21-26)
+    t = rm.par_transform(par_train, par_train)
+    assert np.allclose(t.min(axis=0), -1) and np.allclose(t.max(axis=0), 1)
+    s_tr = np.random.default_rng(0).normal(size=(40, 451)).astype(np.float32)
+    assert np.array_equal(ref.unpreproc(s_tr[:5], s_tr), rm.unpreproc(s_tr[:5], s_tr))
+
+
+def test_predict_squeeze_rule(rm, direct_fixture):
+    f = direct_fixture
+    one = rm.predict(rm.draw_params(1, 3), f["kernels"], f["biases"], f["relu"], f["pmin"], f["pmax"], f["mu"], f["sd"])
+    assert one.shape == (451,)
+    two = rm.predict(rm.draw_params(2, 3), f["kernels"], f["biases"], f["relu"], f["pmin"], f["pmax"], f["mu"], f["sd"])
+    assert two.shape == (2, 451)
+
+
+def test_draw_params_has_exact_zero_fx(rm):
+    p = rm.draw_params(5000, seed=9)
+    assert (p[:, 2] == 0).sum() > 10
+    assert np.all(p[:, 0] > 0) and np.all(p[:, 1] > 0)
