@@ -112,7 +112,7 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 v[i] = __fadd_rn(acc[i][j], b);
-                if (L.relu) v[i] = fmaxf(v[i], 0.f);
+                if (L.relu) v[i] = v[i] < 0.f ? 0.f : v[i];  // NaN propagates like np.maximum / tf.nn.relu
             }
             float4* dst = reinterpret_cast<float4*>(outbuf + n * LDA + 8 * warp);
             dst[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -133,7 +133,7 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         float v = __fadd_rn(acc[i][j], b);
-                        if (L.relu) v = fmaxf(v, 0.f);
+                        if (L.relu) v = v < 0.f ? 0.f : v;
                         v = __fadd_rn(__fmul_rn(v, nc.sd), mu);
                         const float r = (v - ob) * is;
                         part[i] = fmaf(r, r, part[i]);
@@ -165,7 +165,7 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
                         const long long row = rbase + i;
                         if (row < a.n) {
                             float v = __fadd_rn(acc[i][j], b);
-                            if (L.relu) v = fmaxf(v, 0.f);
+                            if (L.relu) v = v < 0.f ? 0.f : v;
                             if (denorm) v = __fadd_rn(__fmul_rn(v, nc.sd), mu);  // preprocess.py:44-45
                             __stcs(a.out + row * N + n, v);
                         }

@@ -1,0 +1,294 @@
+// tcgen05 probe: validates, on a real B200, the encodings the tensor-core kernel relies on --
+// shared-memory matrix descriptors for the un-swizzled K-major "[k/8][row][8]" operand image,
+// the kind::f16 instruction descriptor, A-from-TMEM packing, tcgen05.ld/st 32x32b, tcgen05.commit ->
+// mbarrier, 1-D bulk (TMA) loads with complete_tx and bulk stores.
+//
+//   umma_probe <variant>      one variant per process (a fault in one must not poison the next)
+//
+// Each variant computes D[128,N] = A[128,K] * B[N,K]^T with exactly representable inputs and
+// compares with a host result bit for bit.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#define CK(x)                                                                                   \
+    do {                                                                                        \
+        cudaError_t e = (x);                                                                    \
+        if (e != cudaSuccess) {                                                                 \
+            printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__);     \
+            return 2;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+struct Variant {
+    int N, K;
+    int swap_lbo_sbo;  // 0: LBO = k-group stride, SBO = 8-row-group stride (expected); 1: swapped
+    int a_tmem;        // 1: A operand from TMEM (packed pairs), 0: from smem descriptor
+    int fp16;          // 0 bf16, 1 fp16
+    int bulk_b;        // 1: B image via cp.async.bulk + mbarrier tx, 0: thread copies
+    int bulk_out;      // 1: D staged in smem and written with a bulk store
+    int passes;        // number of accumulate passes over K (3 = hi/lo split style accumulate)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= 1ull << 46;  // descriptor version 1 (Blackwell)
+    return d;         // base offset 0, lbo mode 0, layout type 0 = SWIZZLE_NONE
+}
+
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* flag, int code) {
+    uint32_t addr = smem_u32(bar);
+    for (long long it = 0; it < (1ll << 24); ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    if (flag) atomicExch(flag, code);
+    return false;
+}
+
+__global__ void __launch_bounds__(128, 1)
+probe_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ Bimg, float* __restrict__ D, Variant v, int* flag) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int N = v.N, K = v.K;
+    uint16_t* sA = reinterpret_cast<uint16_t*>(smem);
+    uint16_t* sB = sA + 128 * K;
+    float* sOut = reinterpret_cast<float*>(sB + N * K);  // [128][N] staging for the bulk store
+    __shared__ __align__(8) uint64_t bar_mma, bar_tma;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    for (int e = tid; e < 128 * K; e += 128) {
+        const int m = e / K, k = e - m * K;
+        sA[((k >> 3) * 128 + m) * 8 + (k & 7)] = A[e];
+    }
+    if (!v.bulk_b)
+        for (int e = tid; e < N * K; e += 128) sB[e] = Bimg[e];
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_mma)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_tma)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tm = tmem_base_s;
+
+    if (v.bulk_b) {
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(N * K * 2);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&bar_tma)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(sB)),
+                         "l"(Bimg), "r"(bytes), "r"(smem_u32(&bar_tma))
+                         : "memory");
+        }
+        if (!mbar_wait(&bar_tma, 0, flag, 11)) return;
+    }
+
+    const uint32_t tmemA = 256;  // column offset of the packed A operand
+    if (v.a_tmem) {
+        // thread = row; pack k pairs: low half = even k
+        for (int c = 0; c < K / 2; c += 8) {
+            uint32_t r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = 2 * (c + i);
+                r[i] = (uint32_t)A[tid * K + k] | ((uint32_t)A[tid * K + k + 1] << 16);
+            }
+            const uint32_t addr = tm + ((uint32_t)(warp * 32) << 16) + tmemA + c;
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(addr), "r"(r[0]),
+                         "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                         : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+    }
+
+    if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t idesc = (1u << 4) | ((v.fp16 ? 0u : 1u) << 7) | ((v.fp16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) |
+                               ((uint32_t)(128 >> 4) << 24);
+        const uint32_t a_kg = 128 * 16, b_kg = (uint32_t)N * 16;  // bytes between k-groups of 8
+        uint32_t acc = 0;
+        for (int pass = 0; pass < v.passes; ++pass) {
+            for (int ks = 0; ks < K / 16; ++ks) {
+                const uint64_t db = v.swap_lbo_sbo ? make_desc(smem_u32(sB) + ks * 2 * b_kg, 128, b_kg)
+                                                   : make_desc(smem_u32(sB) + ks * 2 * b_kg, b_kg, 128);
+                if (v.a_tmem) {
+                    const uint32_t ta = tm + tmemA + ks * 8;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tm),
+                        "r"(ta), "l"(db), "r"(idesc), "r"(acc)
+                        : "memory");
+                } else {
+                    const uint64_t da = v.swap_lbo_sbo ? make_desc(smem_u32(sA) + ks * 2 * a_kg, 128, a_kg)
+                                                       : make_desc(smem_u32(sA) + ks * 2 * a_kg, a_kg, 128);
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tm),
+                        "l"(da), "l"(db), "r"(idesc), "r"(acc)
+                        : "memory");
+                }
+                acc = 1;
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar_mma)) : "memory");
+    }
+    if (!mbar_wait(&bar_mma, 0, flag, 12)) return;
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+
+    for (int c = 0; c < N; c += 8) {
+        uint32_t r[8];
+        const uint32_t addr = tm + ((uint32_t)(warp * 32) << 16) + c;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(addr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (v.bulk_out)
+                sOut[tid * N + c + i] = __uint_as_float(r[i]);
+            else
+                D[tid * N + c + i] = __uint_as_float(r[i]);
+        }
+    }
+    if (v.bulk_out) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(D), "r"(smem_u32(sOut)),
+                         "r"((uint32_t)(128 * N * 4))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512));
+    (void)lane;
+}
+
+static uint16_t to16(float x, int fp16) {
+    if (fp16) {
+        __half h = __float2half_rn(x);
+        uint16_t u;
+        memcpy(&u, &h, 2);
+        return u;
+    }
+    __nv_bfloat16 b = __float2bfloat16_rn(x);
+    uint16_t u;
+    memcpy(&u, &b, 2);
+    return u;
+}
+
+int main(int argc, char** argv) {
+    const Variant table[] = {
+        // N,   K, swap, a_tmem, fp16, bulk_b, bulk_out, passes
+        {64, 16, 0, 0, 0, 0, 0, 1},    // 0 smallest: one MMA, expected LBO/SBO
+        {64, 16, 1, 0, 0, 0, 0, 1},    // 1 swapped LBO/SBO
+        {176, 64, 0, 0, 0, 0, 0, 1},   // 2 four k-steps, N = 176
+        {176, 64, 0, 0, 0, 1, 0, 1},   // 3 + B via bulk copy
+        {176, 64, 0, 1, 0, 1, 0, 1},   // 4 A from TMEM
+        {80, 352, 0, 1, 0, 1, 0, 3},   // 5 TS, K = 352, 3 accumulate passes
+        {224, 288, 0, 0, 1, 1, 1, 3},  // 6 SS fp16, N = 224, bulk store of D
+        {144, 16, 0, 0, 0, 1, 0, 1},   // 7 N = 144 (layer-0 style)
+        {176, 64, 1, 0, 0, 0, 0, 1},   // 8 swapped on a bigger case
+        {128, 224, 0, 1, 1, 1, 1, 3},  // 9 TS fp16 + bulk store
+    };
+    const int nvar = sizeof(table) / sizeof(table[0]);
+    if (argc < 2) {
+        printf("%d\n", nvar);
+        return 0;
+    }
+    const int vi = atoi(argv[1]);
+    if (vi < 0 || vi >= nvar) return 1;
+    const Variant v = table[vi];
+    const int N = v.N, K = v.K;
+    std::vector<float> Af(128 * K), Bf(N * K);
+    std::vector<uint16_t> A(128 * K), Bimg(N * K);
+    uint32_t s = 12345u + vi;
+    auto rnd = [&]() {
+        s = s * 1664525u + 1013904223u;
+        return (float)((int)((s >> 16) % 17) - 8) / 8.0f;  // multiples of 1/8 in [-1, 1]
+    };
+    for (auto& x : Af) x = rnd();
+    for (auto& x : Bf) x = rnd();
+    for (int i = 0; i < 128 * K; ++i) A[i] = to16(Af[i], v.fp16);
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) Bimg[((k >> 3) * N + n) * 8 + (k & 7)] = to16(Bf[n * K + k], v.fp16);
+    std::vector<float> ref(128 * N, 0.f);
+    for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < N; ++n) {
+            float acc = 0;
+            for (int k = 0; k < K; ++k) acc += Af[m * K + k] * Bf[n * K + k];
+            ref[m * N + n] = acc * v.passes;
+        }
+    uint16_t *dA, *dB;
+    float* dD;
+    int* dflag;
+    CK(cudaMalloc(&dA, A.size() * 2));
+    CK(cudaMalloc(&dB, Bimg.size() * 2));
+    CK(cudaMalloc(&dD, ref.size() * 4));
+    CK(cudaMalloc(&dflag, 4));
+    CK(cudaMemset(dflag, 0, 4));
+    CK(cudaMemset(dD, 0xff, ref.size() * 4));
+    CK(cudaMemcpy(dA, A.data(), A.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, Bimg.data(), Bimg.size() * 2, cudaMemcpyHostToDevice));
+    const size_t smem = (size_t)128 * K * 2 + (size_t)N * K * 2 + (v.bulk_out ? (size_t)128 * N * 4 : 0) + 1024;
+    CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    if (smem > 226 * 1024) {
+        printf("variant %d: smem %zu too large\n", vi, smem);
+        return 1;
+    }
+    probe_kernel<<<1, 128, smem>>>(dA, dB, dD, v, dflag);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    std::vector<float> out(ref.size());
+    int flag = 0;
+    CK(cudaMemcpy(out.data(), dD, out.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&flag, dflag, 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0;
+    int bad = 0;
+    for (size_t i = 0; i < ref.size(); ++i) {
+        double e = fabs((double)out[i] - ref[i]);
+        if (!(e <= 0)) ++bad;
+        if (e > maxerr || e != e) maxerr = e != e ? 1e30 : e;
+    }
+    printf("variant %d N=%d K=%d swap=%d a_tmem=%d fp16=%d bulk_b=%d bulk_out=%d passes=%d : flag=%d mismatches=%d/%zu maxerr=%g  %s\n", vi, N,
+           K, v.swap_lbo_sbo, v.a_tmem, v.fp16, v.bulk_b, v.bulk_out, v.passes, flag, bad, ref.size(), maxerr,
+           (bad == 0 && flag == 0) ? "PASS" : "FAIL");
+    if (bad) {
+        int shown = 0;
+        for (size_t i = 0; i < ref.size() && shown < 6; ++i)
+            if (out[i] != ref[i]) {
+                printf("   [m=%zu n=%zu] got %g want %g\n", i / N, i % N, out[i], ref[i]);
+                ++shown;
+            }
+    }
+    return (bad == 0 && flag == 0) ? 0 : 3;
+}
