@@ -1,19 +1,700 @@
-// tcgen05/TMEM tensor-core path -- placeholder until the kernel lands.
+// tcgen05 / TMEM tensor-core path of the fused emulator kernel (sm_100a).
+//
+// One persistent CTA per SM processes 128-row tiles.  All Dense layers of a tile are chained
+// on-chip: every layer is a sequence of tcgen05.mma (kind::f16, M=128, fp32 accumulate in TMEM)
+// in a 3-pass split  D += A_hi*W_hi + A_hi*W_lo + A_lo*W_hi  (bf16 or fp16 hi/lo pairs), the
+// epilogue warps read the accumulators back with tcgen05.ld, add bias, apply ReLU, split the
+// result into hi/lo again and hand it to the next layer either through shared memory (UMMA
+// "SS" operand) or -- converted IN PLACE over the accumulator columns -- through TMEM (UMMA
+// "TS" operand).  Weights (1.5 MB of packed hi/lo operand images, L2 resident) stream through a
+// ring of shared-memory stages filled by 1-D bulk (TMA) copies.  The first layer's operand
+// comes from the fused parameter transform, the last layer's epilogue applies the output
+// transform (or the chi^2 reduction) and writes coalesced row segments.
+//
+// Warp roles (192 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer (one thread) and
+// TMEM allocator, warps 2..5 = epilogue (thread = tile row = TMEM lane).
+//
+// Operand images (validated on hardware by tools/umma_probe.cu):
+//   un-swizzled K-major core-matrix layout [k/8][row][8 x 16-bit]: descriptor LBO = bytes between
+//   k-groups, SBO = 128 B between 8-row groups, version 1, layout type 0;
+//   A in TMEM: lane = row, one 32-bit column per k pair (even k in the low half).
+//
+// Reference semantics: VeryAccurateEmulator/emulator.py:401-403 (see fp32_kernel.cuh for the
+// bit-faithful path; this one is held to 0.01 mK rms / 0.05 mK max).
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstring>
 #include <string>
 #include <vector>
+
 #include "common.cuh"
 
 namespace tck {
-struct Plan { int dummy; };
-inline bool build_plan(int, const int*, const float* const*, const float* const*, const int*, Plan&,
-                       std::vector<unsigned short>*, std::vector<float>&, std::string& why) {
-    why = "tensor-core kernel not built yet";
-    return false;
+
+constexpr int MT = 128;
+constexpr int NTHREADS = 192;
+constexpr int MAXL = 8;
+constexpr int MAXC = 32;
+constexpr int NFULL = 4;          // ring of "accumulator chunk ready" barriers
+constexpr int MAX_SLOTS = 8;
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int KSTEP_BYTES = 8192; // one k-step (16 features) of a 128-row activation tile: hi 4 KB + lo 4 KB
+constexpr int A_KG_BYTES = 2048;  // 128 rows x 16 B: distance between the two k-groups of a k-step
+
+enum : int { A_SMEM_A0 = 0, A_SMEM_ACT = 1, A_TMEM = 2 };
+enum : int { DST_SMEM = 0, DST_TMEM = 1, DST_FINAL = 2 };
+
+struct Layer {
+    int K;         // input width padded to 16
+    int N;         // true output width
+    int Npad;      // padded to 16
+    int relu;
+    int a_src;     // A_*
+    int out_dst;   // DST_*
+    int bias_off;  // float offset into the bias image / smem copy
+    int first_chunk, nchunks;
+};
+
+struct Chunk {
+    int layer;
+    int n0, ncols;   // column range of the layer this chunk accumulates
+    int dcol;        // TMEM column of the accumulator
+    int qbuf;        // 0/1: ring buffer index, -1: in place (stays in TMEM as next layer's operand)
+    int nstages;     // weight stages (each 16 k wide, hi+lo) == K/16
+    unsigned w_off;  // byte offset of the first stage in the weight image
+};
+
+struct Plan {
+    int n_layers, n_chunks;
+    int K0;      // true number of input parameters
+    int n_out;   // true output width
+    int slot_bytes, nslots;
+    int bias_total;
+    // shared-memory carve-up (bytes from the 1024-aligned base)
+    int off_act, off_a0, off_ring, off_bias, off_s0, off_obs, off_isig, off_bar, smem_total;
+    unsigned w_bytes;
+    Layer L[MAXL];
+    Chunk C[MAXC];
+};
+
+// ---------------------------------------------------------------------------------------------
+// Host: planning and weight packing
+// ---------------------------------------------------------------------------------------------
+inline unsigned short f2bf16(float x) {
+    __nv_bfloat16 b = __float2bfloat16_rn(x);
+    unsigned short u;
+    std::memcpy(&u, &b, 2);
+    return u;
 }
-inline cudaError_t prepare() { return cudaSuccess; }
-inline cudaError_t launch(const Plan&, const NormConsts&, const LaunchArgs&, const void*, const float*, int, int,
-                          cudaStream_t) {
-    return cudaErrorNotSupported;
+inline float bf162f(unsigned short u) {
+    unsigned int w = static_cast<unsigned int>(u) << 16;
+    float f;
+    std::memcpy(&f, &w, 4);
+    return f;
 }
+inline unsigned short f2h16(float x) {
+    __half h = __float2half_rn(x);
+    unsigned short u;
+    std::memcpy(&u, &h, 2);
+    return u;
+}
+inline float h162f(unsigned short u) {
+    __half h;
+    std::memcpy(&h, &u, 2);
+    return __half2float(h);
+}
+
+// Build the schedule for a Dense stack.  Returns false (with `why`) when the stack does not fit.
+inline bool build_plan(int n_layers, const int* dims, const float* const* kernels, const float* const* biases,
+                       const int* relu, Plan& P, std::vector<unsigned short>* img /*[2]: bf16, fp16*/,
+                       std::vector<float>& bias_img, std::string& why) {
+    P = Plan{};
+    if (n_layers < 2 || n_layers > MAXL) { why = "needs 2.." + std::to_string(MAXL) + " layers"; return false; }
+    if (relu[n_layers - 1]) { why = "last layer must be linear"; return false; }
+    if (dims[0] > 16) { why = "more than 16 input parameters"; return false; }
+    P.n_layers = n_layers;
+    P.K0 = dims[0];
+    P.n_out = dims[n_layers];
+    auto pad16 = [](int x) { return (x + 15) / 16 * 16; };
+
+    int smem_w = 0, tmem_w = 0;  // widest activation resident in smem / tmem
+    int boff = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        Layer& L = P.L[l];
+        L.K = pad16(dims[l]);
+        L.N = dims[l + 1];
+        L.Npad = pad16(L.N);
+        L.relu = relu[l] ? 1 : 0;
+        L.a_src = (l == 0) ? A_SMEM_A0 : ((l & 1) ? A_SMEM_ACT : A_TMEM);
+        L.out_dst = (l == n_layers - 1) ? DST_FINAL : ((l & 1) ? DST_TMEM : DST_SMEM);
+        L.bias_off = boff;
+        boff += L.Npad;
+        if (L.out_dst == DST_SMEM) smem_w = std::max(smem_w, L.Npad);
+        if (L.out_dst == DST_TMEM) tmem_w = std::max(tmem_w, L.Npad);
+        if (l > 0 && L.K != P.L[l - 1].Npad) { why = "internal: width mismatch"; return false; }
+    }
+    P.bias_total = boff;
+    if (tmem_w > 480) { why = "a TMEM-resident hidden layer is wider than 480"; return false; }
+
+    // accumulator placement
+    const int last = n_layers - 1;
+    auto qgeom = [&](int l, int& q0, int& qsize) {
+        // columns free for ring accumulators while layer l runs: everything above its TMEM operand
+        int lo = (P.L[l].a_src == A_TMEM) ? P.L[l].K : 0;
+        qsize = ((512 - lo) / 2) / 16 * 16;
+        if (qsize > 256) qsize = 256;
+        q0 = 512 - 2 * qsize;
+    };
+    int nchunks = 0;
+    unsigned woff = 0;
+    int qflip = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        Layer& L = P.L[l];
+        L.first_chunk = nchunks;
+        const int units = L.Npad / 16;
+        int maxcols, q0 = 0, qsize = 0;
+        if (L.out_dst == DST_TMEM) {
+            maxcols = 224;  // stage = ncols * 16 k * 2 B * (hi + lo) <= 14336 B
+            if (L.Npad > 512) { why = "in-place layer too wide"; return false; }
+        } else {
+            // layer 0 shares the ring geometry of the last layer (their accumulators overlap in
+            // time across consecutive tiles without a drain in between)
+            qgeom(l == 0 ? last : l, q0, qsize);
+            if (l == 0 && P.L[last].a_src != A_TMEM) qgeom(last, q0, qsize);
+            maxcols = std::min(qsize, 224);
+            if (maxcols < 16) { why = "no TMEM left for accumulators"; return false; }
+        }
+        const int nch = (L.Npad + maxcols - 1) / maxcols;
+        int done_units = 0;
+        for (int c = 0; c < nch; ++c) {
+            if (nchunks >= MAXC) { why = "too many accumulator chunks"; return false; }
+            Chunk& C = P.C[nchunks];
+            const int u = (units - done_units + (nch - c) - 1) / (nch - c);  // balanced, larger first
+            C.layer = l;
+            C.n0 = done_units * 16;
+            C.ncols = u * 16;
+            if (L.out_dst == DST_TMEM) {
+                C.qbuf = -1;
+                C.dcol = C.n0;
+            } else {
+                C.qbuf = qflip;
+                C.dcol = q0 + qflip * qsize;
+                qflip ^= 1;
+            }
+            C.nstages = L.K / 16;
+            C.w_off = woff;
+            woff += static_cast<unsigned>(C.nstages) * C.ncols * 16 * 2 * 2;
+            done_units += u;
+            ++nchunks;
+        }
+        L.nchunks = nch;
+    }
+    // every tile must use each ring buffer an even... no: parity is tracked with running counters.
+    P.n_chunks = nchunks;
+    P.w_bytes = woff;
+    P.slot_bytes = 0;
+    for (int c = 0; c < nchunks; ++c) P.slot_bytes = std::max(P.slot_bytes, P.C[c].ncols * 16 * 2 * 2);
+
+    // shared memory
+    int off = 0;
+    P.off_act = off;
+    off += std::max(smem_w / 16 * KSTEP_BYTES, 4 * 32 * 17 * 4 /* output transpose staging aliases this */);
+    P.off_a0 = off;
+    off += KSTEP_BYTES;
+    P.off_bias = off;
+    off += P.bias_total * 4;
+    const int nop = pad16(P.n_out);
+    P.off_s0 = off;
+    off += nop * 4;
+    P.off_obs = off;
+    off += nop * 4;
+    P.off_isig = off;
+    off += nop * 4;
+    P.off_bar = off;
+    off += 256;
+    off = (off + 127) / 128 * 128;
+    P.off_ring = off;
+    const int avail = SMEM_LIMIT - 128 /*alignment slack*/ - off;
+    P.nslots = std::min(MAX_SLOTS, avail / P.slot_bytes);
+    if (P.nslots < 2) { why = "shared memory: activations leave no room for a weight ring"; return false; }
+    off += P.nslots * P.slot_bytes;
+    P.smem_total = off + 128;
+
+    // weight image, in exactly the order the MMA warp consumes it: chunk -> k-step -> {hi, lo} tile
+    // tile = [2 k-groups][ncols rows][8 elements]  (B operand, "K-major": row n holds W[k][n])
+    for (int f = 0; f < 2; ++f) img[f].assign(P.w_bytes / 2, 0);
+    for (int c = 0; c < nchunks; ++c) {
+        const Chunk& C = P.C[c];
+        const int l = C.layer;
+        const int Kt = dims[l], Nt = dims[l + 1];
+        for (int s = 0; s < C.nstages; ++s) {
+            const size_t base = (C.w_off + static_cast<size_t>(s) * C.ncols * 64) / 2;  // in elements
+            const size_t lo_base = base + static_cast<size_t>(C.ncols) * 16;
+            for (int kk = 0; kk < 16; ++kk) {
+                const int k = s * 16 + kk;
+                for (int nn = 0; nn < C.ncols; ++nn) {
+                    const int n = C.n0 + nn;
+                    const float w = (k < Kt && n < Nt) ? kernels[l][static_cast<size_t>(k) * Nt + n] : 0.f;
+                    const size_t e = (static_cast<size_t>(kk >> 3) * C.ncols + nn) * 8 + (kk & 7);
+                    const unsigned short hb = f2bf16(w);
+                    img[0][base + e] = hb;
+                    img[0][lo_base + e] = f2bf16(w - bf162f(hb));
+                    const unsigned short hh = f2h16(w);
+                    img[1][base + e] = hh;
+                    img[1][lo_base + e] = f2h16(w - h162f(hh));
+                }
+            }
+        }
+    }
+    bias_img.assign(P.bias_total, 0.f);
+    for (int l = 0; l < n_layers; ++l)
+        for (int n = 0; n < dims[l + 1]; ++n) bias_img[P.L[l].bias_off + n] = biases[l][n];
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    unsigned spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((++spins & 1023u) == 0) {  // deadlock guard: a scheduling bug must fault, not hang the GPU
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000ll) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return static_cast<uint64_t>((saddr & 0x3FFFF) >> 4) | (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
+        "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t ta, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d),
+        "r"(ta), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+__device__ __forceinline__ float relu_nan(float v) {  // max that propagates NaN like np.maximum / tf.nn.relu
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;\n" : "=f"(r) : "f"(v), "f"(0.f));
+    return r;
+}
+
+// Split two fp32 values into packed 16-bit hi and lo words (element 0 in the low half).
+template <int FMT>
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    if (FMT == 0) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        hi = *reinterpret_cast<uint32_t*>(&h);
+        const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+        __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+        lo = *reinterpret_cast<uint32_t*>(&l);
+    } else {
+        __half2 h = __floats2half2_rn(a, b);
+        hi = *reinterpret_cast<uint32_t*>(&h);
+        const float2 hf = __half22float2(h);
+        __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+        lo = *reinterpret_cast<uint32_t*>(&l);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The kernel
+// ---------------------------------------------------------------------------------------------
+template <int FMT>  // 0: bf16 split, 1: fp16 split
+__global__ void __launch_bounds__(NTHREADS, 1)
+vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormConsts nc, const __grid_constant__ LaunchArgs a,
+                const uint8_t* __restrict__ wimg, const float* __restrict__ bias_g) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 127u) & ~127u;  // shared-window address of the carve-up
+    uint8_t* sm = smem_raw + (base - raw);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long ntiles = (a.n + MT - 1) / MT;
+
+    // barrier addresses
+    const uint32_t bar0 = base + P.off_bar;
+    auto bar_ring_full = [&](int s) { return bar0 + 8u * s; };
+    auto bar_ring_empty = [&](int s) { return bar0 + 8u * (MAX_SLOTS + s); };
+    auto bar_chunk_full = [&](int i) { return bar0 + 8u * (2 * MAX_SLOTS + i); };
+    auto bar_q_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + NFULL + b); };
+    const uint32_t bar_act_ready = bar0 + 8u * (2 * MAX_SLOTS + NFULL + 2);
+    const uint32_t bar_a0_ready = bar0 + 8u * (2 * MAX_SLOTS + NFULL + 3);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + P.off_bar + 8 * (2 * MAX_SLOTS + NFULL + 4));
+
+    float* s_bias = reinterpret_cast<float*>(sm + P.off_bias);
+    float* s_s0 = reinterpret_cast<float*>(sm + P.off_s0);
+    float* s_obs = reinterpret_cast<float*>(sm + P.off_obs);
+    float* s_isig = reinterpret_cast<float*>(sm + P.off_isig);
+
+    // ---- one-time setup -------------------------------------------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < P.nslots; ++s) {
+            mbar_init(bar_ring_full(s), 1);
+            mbar_init(bar_ring_empty(s), 1);
+        }
+        for (int i = 0; i < NFULL; ++i) mbar_init(bar_chunk_full(i), 1);
+        for (int b = 0; b < 2; ++b) mbar_init(bar_q_empty(b), 128);
+        mbar_init(bar_act_ready, 128);
+        mbar_init(bar_a0_ready, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    {
+        const Layer& LL = P.L[P.n_layers - 1];
+        const int nop = LL.Npad;
+        for (int i = tid; i < P.bias_total; i += NTHREADS) s_bias[i] = bias_g[i];
+        for (int n = tid; n < nop; n += NTHREADS) {
+            const float b = bias_g[LL.bias_off + n];
+            float s0 = b, ob = 0.f, is = 0.f;
+            if (n < P.n_out) {
+                if (a.out_mode != OUT_NORMALISED) s0 = fmaf(b, nc.sd, a.mu[n]);
+                if (a.out_mode == OUT_CHI2) {
+                    ob = a.obs[n];
+                    is = a.isig[n];
+                }
+            }
+            s_s0[n] = s0;
+            s_obs[n] = ob;
+            s_isig[n] = is;
+        }
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== producer: stream the weight image through the ring ============
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t phase = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int c = 0; c < P.n_chunks; ++c) {
+                    const Chunk& C = P.C[c];
+                    const uint32_t bytes = static_cast<uint32_t>(C.ncols) * 64u;
+                    const uint8_t* src = wimg + C.w_off;
+                    for (int s = 0; s < C.nstages; ++s) {
+                        mbar_wait(bar_ring_empty(slot), phase ^ 1u);
+                        mbar_expect_tx(bar_ring_full(slot), bytes);
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                                base + P.off_ring + slot * P.slot_bytes),
+                            "l"(src + static_cast<size_t>(s) * bytes), "r"(bytes), "r"(bar_ring_full(slot))
+                            : "memory");
+                        if (++slot == P.nslots) {
+                            slot = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer ====================================================
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t rphase = 0;
+            uint32_t seq = 0;              // running chunk counter (chunk_full ring)
+            uint32_t q_use0 = 0, q_use1 = 0;  // uses so far of each ring accumulator
+            uint32_t act_cnt = 0, a0_cnt = 0;
+            const uint32_t fmtbits = (FMT == 0) ? 1u : 0u;
+            const uint32_t idesc_base = (1u << 4) | (fmtbits << 7) | (fmtbits << 10) | ((128u >> 4) << 24);
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int c = 0; c < P.n_chunks; ++c) {
+                    const Chunk& C = P.C[c];
+                    const Layer& L = P.L[C.layer];
+                    if (c == L.first_chunk) {  // this layer's A operand must be complete
+                        if (C.layer == 0) {
+                            mbar_wait(bar_a0_ready, a0_cnt & 1u);
+                            ++a0_cnt;
+                        } else {
+                            mbar_wait(bar_act_ready, act_cnt & 1u);
+                            ++act_cnt;
+                        }
+                        tc_fence_after();
+                    }
+                    if (C.qbuf >= 0) {  // accumulator buffer must have been drained by the epilogue
+                        const uint32_t u = C.qbuf ? q_use1 : q_use0;
+                        if (C.qbuf) ++q_use1; else ++q_use0;
+                        if (u > 0) {
+                            mbar_wait(bar_q_empty(C.qbuf), (u - 1u) & 1u);
+                            tc_fence_after();
+                        }
+                    }
+                    const uint32_t idesc = idesc_base | (static_cast<uint32_t>(C.ncols >> 3) << 17);
+                    const uint32_t d = tm + static_cast<uint32_t>(C.dcol);
+                    const uint32_t b_kg = static_cast<uint32_t>(C.ncols) * 16u;  // bytes between B k-groups
+                    const uint32_t b_lo = b_kg * 2u;                             // hi tile -> lo tile
+                    const uint32_t a_base = base + (L.a_src == A_SMEM_A0 ? P.off_a0 : P.off_act);
+                    for (int s = 0; s < C.nstages; ++s) {
+                        mbar_wait(bar_ring_full(slot), rphase);
+                        tc_fence_after();
+                        const uint32_t bs = base + P.off_ring + slot * P.slot_bytes;
+                        const uint64_t db_hi = make_desc(bs, b_kg, 128);
+                        const uint64_t db_lo = make_desc(bs + b_lo, b_kg, 128);
+                        const uint32_t acc0 = s > 0 ? 1u : 0u;
+                        if (L.a_src == A_TMEM) {
+                            const uint32_t ta_hi = tm + static_cast<uint32_t>(s * 16);
+                            const uint32_t ta_lo = ta_hi + 8u;
+                            mma_ts(d, ta_hi, db_hi, idesc, acc0);
+                            mma_ts(d, ta_hi, db_lo, idesc, 1u);
+                            mma_ts(d, ta_lo, db_hi, idesc, 1u);
+                        } else {
+                            const uint32_t as = a_base + s * KSTEP_BYTES;
+                            const uint64_t da_hi = make_desc(as, A_KG_BYTES, 128);
+                            const uint64_t da_lo = make_desc(as + 2 * A_KG_BYTES, A_KG_BYTES, 128);
+                            mma_ss(d, da_hi, db_hi, idesc, acc0);
+                            mma_ss(d, da_hi, db_lo, idesc, 1u);
+                            mma_ss(d, da_lo, db_hi, idesc, 1u);
+                        }
+                        mma_commit(bar_ring_empty(slot));  // frees the stage when these MMAs have read it
+                        if (++slot == P.nslots) {
+                            slot = 0;
+                            rphase ^= 1u;
+                        }
+                    }
+                    mma_commit(bar_chunk_full(seq & (NFULL - 1)));
+                    ++seq;
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue warps (thread = row) ==================================
+        const int sub = warp & 3;                 // TMEM sub-partition this warp may access
+        const int row = sub * 32 + lane;          // tile row == TMEM lane
+        const uint32_t tlane = static_cast<uint32_t>(sub * 32) << 16;
+        float* stage = reinterpret_cast<float*>(sm + P.off_act) + (warp - 2) * (32 * 17);
+        const Layer& LL = P.L[P.n_layers - 1];
+        const int NO = P.n_out;
+        uint32_t seq = 0;
+
+        auto write_a0 = [&](long long tile) {
+            // fused parameter transform (preprocess.py:74-78, :105-108) -> layer-0 operand (k padded to 16)
+            const long long grow = tile * MT + row;
+            float x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = 0.f;
+            if (grow < a.n) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (j < P.K0) {
+                        const long long g = grow * P.K0 + j;
+                        if (a.in_mode == IN_PARAMS_F64)
+                            x[j] = transform_param(reinterpret_cast<const double*>(a.in)[g], j, nc, false);
+                        else if (a.in_mode == IN_PARAMS_F32)
+                            x[j] = transform_param(static_cast<double>(reinterpret_cast<const float*>(a.in)[g]), j, nc, true);
+                        else
+                            x[j] = reinterpret_cast<const float*>(a.in)[g];
+                    }
+                }
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) split2<FMT>(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
+            uint8_t* a0 = sm + P.off_a0;
+            *reinterpret_cast<uint4*>(a0 + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(a0 + A_KG_BYTES + row * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            *reinterpret_cast<uint4*>(a0 + 2 * A_KG_BYTES + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(a0 + 3 * A_KG_BYTES + row * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            fence_async_smem();
+            mbar_arrive(bar_a0_ready);
+        };
+
+        if (static_cast<long long>(blockIdx.x) < ntiles) write_a0(blockIdx.x);
+
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const long long grow = tile * MT + row;
+            float chi = 0.f;
+            for (int c = 0; c < P.n_chunks; ++c) {
+                const Chunk& C = P.C[c];
+                const Layer& L = P.L[C.layer];
+                mbar_wait(bar_chunk_full(seq & (NFULL - 1)), (seq / NFULL) & 1u);
+                ++seq;
+                tc_fence_after();
+                const float* bl = s_bias + L.bias_off + C.n0;
+                for (int g = 0; g < C.ncols / 16; ++g) {
+                    uint32_t r[16];
+                    const uint32_t taddr = tm + tlane + static_cast<uint32_t>(C.dcol + 16 * g);
+                    tmem_ld16(taddr, r);
+                    tmem_ld_wait();
+                    if (L.out_dst != DST_FINAL) {
+                        uint32_t w[16];  // [0..7] hi words, [8..15] lo words
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bl + 16 * g + 4 * q);
+                            float v0 = __uint_as_float(r[4 * q + 0]) + b4.x;
+                            float v1 = __uint_as_float(r[4 * q + 1]) + b4.y;
+                            float v2 = __uint_as_float(r[4 * q + 2]) + b4.z;
+                            float v3 = __uint_as_float(r[4 * q + 3]) + b4.w;
+                            if (L.relu) {
+                                v0 = relu_nan(v0);
+                                v1 = relu_nan(v1);
+                                v2 = relu_nan(v2);
+                                v3 = relu_nan(v3);
+                            }
+                            split2<FMT>(v0, v1, w[2 * q], w[8 + 2 * q]);
+                            split2<FMT>(v2, v3, w[2 * q + 1], w[8 + 2 * q + 1]);
+                        }
+                        if (L.out_dst == DST_TMEM) {
+                            tmem_st16(taddr, w);  // in place: these 16 columns become the next layer's k-step
+                        } else {
+                            uint8_t* dst = sm + P.off_act + ((C.n0 >> 4) + g) * KSTEP_BYTES + row * 16;
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                            *reinterpret_cast<uint4*>(dst + A_KG_BYTES) = make_uint4(w[4], w[5], w[6], w[7]);
+                            *reinterpret_cast<uint4*>(dst + 2 * A_KG_BYTES) = make_uint4(w[8], w[9], w[10], w[11]);
+                            *reinterpret_cast<uint4*>(dst + 3 * A_KG_BYTES) = make_uint4(w[12], w[13], w[14], w[15]);
+                        }
+                    } else {
+                        const int n = C.n0 + 16 * g;
+                        const float s1 = (a.out_mode == OUT_NORMALISED) ? 1.f : nc.sd;
+                        if (a.out_mode == OUT_CHI2) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float v = fmaf(__uint_as_float(r[i]), s1, s_s0[n + i]);
+                                const float rr = (v - s_obs[n + i]) * s_isig[n + i];  // isig = 0 on padding
+                                chi = fmaf(rr, rr, chi);
+                            }
+                        } else {
+                            // 32x16 transpose through this warp's staging tile -> coalesced row segments
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) stage[lane * 17 + i] = fmaf(__uint_as_float(r[i]), s1, s_s0[n + i]);
+                            __syncwarp();
+                            const int cl = lane & 15, rsel = lane >> 4;
+                            const long long rbase = tile * MT + sub * 32;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const int rr = 2 * i + rsel;
+                                const long long gr = rbase + rr;
+                                if (gr < a.n && n + cl < NO) __stcs(a.out + gr * NO + n + cl, stage[rr * 17 + cl]);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+                // publish: operand visible to the tensor pipe / accumulator buffer free
+                if (L.out_dst == DST_SMEM) fence_async_smem();
+                if (L.out_dst == DST_TMEM) tmem_st_wait();
+                tc_fence_before();
+                if (C.qbuf >= 0) mbar_arrive(bar_q_empty(C.qbuf));
+                if (L.out_dst != DST_FINAL && c == L.first_chunk + L.nchunks - 1) mbar_arrive(bar_act_ready);
+                // the layer-0 operand of the NEXT tile can be written as soon as layer 0 of this tile is done
+                if (C.layer == 0 && c == L.first_chunk + L.nchunks - 1) {
+                    const long long nt = tile + gridDim.x;
+                    if (nt < ntiles) write_a0(nt);
+                }
+            }
+            if (a.out_mode == OUT_CHI2) {
+                unsigned long long key = ~0ull;
+                if (grow < a.n) {
+                    if (a.chi2) a.chi2[grow] = chi;
+                    key = pack_min_key(chi, static_cast<unsigned long long>(a.row_base + grow));
+                }
+                if (a.argmin_key) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                        key = other < key ? other : key;
+                    }
+                    if (lane == 0 && key != ~0ull) atomicMin(a.argmin_key, key);
+                }
+            }
+            (void)LL;
+            // the output staging tiles alias the activation buffer: no warp may start writing the next
+            // tile's activations before every epilogue warp is done with its staging tile
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        }
+    }
+
+    // ---- teardown -------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512));
+    }
+}
+
+inline cudaError_t prepare() {
+    cudaError_t e = cudaFuncSetAttribute(vae21_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(vae21_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+}
+
+inline cudaError_t launch(const Plan& P, const NormConsts& nc, const LaunchArgs& a, const void* wimg, const float* bias,
+                          int fmt, int sm_count, cudaStream_t st) {
+    const long long ntiles = (a.n + MT - 1) / MT;
+    if (ntiles == 0) return cudaSuccess;
+    const int grid = static_cast<int>(std::min<long long>(ntiles, sm_count));
+    if (fmt == 0)
+        vae21_tc_kernel<0><<<grid, NTHREADS, P.smem_total, st>>>(P, nc, a, static_cast<const uint8_t*>(wimg), bias);
+    else
+        vae21_tc_kernel<1><<<grid, NTHREADS, P.smem_total, st>>>(P, nc, a, static_cast<const uint8_t*>(wimg), bias);
+    return cudaGetLastError();
+}
+
 }  // namespace tck
