@@ -74,7 +74,7 @@ struct Plan {
     int slot_bytes, nslots;
     int bias_total;
     // shared-memory carve-up (bytes from the 1024-aligned base)
-    int off_act, off_a0, off_ring, off_bias, off_s0, off_obs, off_isig, off_bar, smem_total;
+    int off_act, off_stage, off_a0, off_ring, off_bias, off_s0, off_obs, off_isig, off_bar, smem_total;
     unsigned w_bytes;
     Layer L[MAXL];
     Chunk C[MAXC];
@@ -141,12 +141,20 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
 
     // accumulator placement
     const int last = n_layers - 1;
-    auto qgeom = [&](int l, int& q0, int& qsize) {
-        // columns free for ring accumulators while layer l runs: everything above its TMEM operand
-        int lo = (P.L[l].a_src == A_TMEM) ? P.L[l].K : 0;
-        qsize = ((512 - lo) / 2) / 16 * 16;
-        if (qsize > 256) qsize = 256;
-        q0 = 512 - 2 * qsize;
+    auto qgeom = [&](int l, int& q0, int& qsize, int& nbuf) {
+        // columns free for ring accumulators while layer l runs: everything above its TMEM operand.
+        // Measured MMA cost (tools/umma_probe.cu): A from TMEM max(96, N/2 + 10) cycles, A from smem
+        // N/2 + 43 -- narrow accumulators waste the tensor pipe, so when two buffers would be
+        // narrower than 112 columns use a single wide one (the MMA then alternates with the epilogue).
+        const int lo = (P.L[l].a_src == A_TMEM) ? P.L[l].K : 0;
+        const int freec = 512 - lo;
+        nbuf = 2;
+        qsize = std::min(256, (freec / 2) / 16 * 16);
+        if (qsize < 112) {
+            nbuf = 1;
+            qsize = std::min(256, freec / 16 * 16);
+        }
+        q0 = 512 - nbuf * qsize;
     };
     int nchunks = 0;
     unsigned woff = 0;
@@ -155,15 +163,14 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
         Layer& L = P.L[l];
         L.first_chunk = nchunks;
         const int units = L.Npad / 16;
-        int maxcols, q0 = 0, qsize = 0;
+        int maxcols, q0 = 0, qsize = 0, nbuf = 2;
         if (L.out_dst == DST_TMEM) {
             maxcols = 224;  // stage = ncols * 16 k * 2 B * (hi + lo) <= 14336 B
             if (L.Npad > 512) { why = "in-place layer too wide"; return false; }
         } else {
             // layer 0 shares the ring geometry of the last layer (their accumulators overlap in
             // time across consecutive tiles without a drain in between)
-            qgeom(l == 0 ? last : l, q0, qsize);
-            if (l == 0 && P.L[last].a_src != A_TMEM) qgeom(last, q0, qsize);
+            qgeom(l == 0 ? last : l, q0, qsize, nbuf);
             maxcols = std::min(qsize, 224);
             if (maxcols < 16) { why = "no TMEM left for accumulators"; return false; }
         }
@@ -180,9 +187,10 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
                 C.qbuf = -1;
                 C.dcol = C.n0;
             } else {
-                C.qbuf = qflip;
-                C.dcol = q0 + qflip * qsize;
-                qflip ^= 1;
+                const int b = (nbuf == 1) ? 0 : qflip;
+                C.qbuf = b;
+                C.dcol = q0 + b * qsize;
+                if (nbuf == 2) qflip ^= 1;
             }
             C.nstages = L.K / 16;
             C.w_off = woff;
@@ -201,7 +209,14 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
     // shared memory
     int off = 0;
     P.off_act = off;
-    off += std::max(smem_w / 16 * KSTEP_BYTES, 4 * 32 * 17 * 4 /* output transpose staging aliases this */);
+    off += std::max(smem_w / 16 * KSTEP_BYTES, 4 * 32 * 17 * 4);
+    // The last layer's epilogue transposes through a small staging tile.  It may alias the
+    // activation buffer only when the last layer does not read its A operand from there.
+    P.off_stage = P.off_act;
+    if (P.L[last].a_src == A_SMEM_ACT) {
+        P.off_stage = off;
+        off += 4 * 32 * 17 * 4;
+    }
     P.off_a0 = off;
     off += KSTEP_BYTES;
     P.off_bias = off;
@@ -288,6 +303,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             else if (now - t0 > 8000000000ll) __trap();
         }
     }
+}
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %1;\n\tselp.u32 %0, 1, 0, px;\n\t}\n"
+                 : "=r"(pred)
+                 : "r"(0xffffffffu));
+    return pred;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -455,10 +477,13 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         }
     } else if (warp == 1) {
         // ===================== MMA issuer ====================================================
-        if (lane == 0) {
+        // The whole warp runs this (warp-uniform) loop and only the tcgen05 instructions are
+        // predicated on one elected lane: measured with tools/umma_probe.cu, a loop inside an
+        // `if (lane == 0)` branch costs 269 cycles per MMA, this form 96..131.
+        {
             int slot = 0;
             uint32_t rphase = 0;
-            uint32_t seq = 0;              // running chunk counter (chunk_full ring)
+            uint32_t seq = 0;                 // running chunk counter (chunk_full ring)
             uint32_t q_use0 = 0, q_use1 = 0;  // uses so far of each ring accumulator
             uint32_t act_cnt = 0, a0_cnt = 0;
             const uint32_t fmtbits = (FMT == 0) ? 1u : 0u;
@@ -475,21 +500,19 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                             mbar_wait(bar_act_ready, act_cnt & 1u);
                             ++act_cnt;
                         }
-                        tc_fence_after();
                     }
                     if (C.qbuf >= 0) {  // accumulator buffer must have been drained by the epilogue
                         const uint32_t u = C.qbuf ? q_use1 : q_use0;
                         if (C.qbuf) ++q_use1; else ++q_use0;
-                        if (u > 0) {
-                            mbar_wait(bar_q_empty(C.qbuf), (u - 1u) & 1u);
-                            tc_fence_after();
-                        }
+                        if (u > 0) mbar_wait(bar_q_empty(C.qbuf), (u - 1u) & 1u);
                     }
+                    tc_fence_after();
                     const uint32_t idesc = idesc_base | (static_cast<uint32_t>(C.ncols >> 3) << 17);
                     const uint32_t d = tm + static_cast<uint32_t>(C.dcol);
                     const uint32_t b_kg = static_cast<uint32_t>(C.ncols) * 16u;  // bytes between B k-groups
                     const uint32_t b_lo = b_kg * 2u;                             // hi tile -> lo tile
                     const uint32_t a_base = base + (L.a_src == A_SMEM_A0 ? P.off_a0 : P.off_act);
+                    const bool ts = (L.a_src == A_TMEM);
                     for (int s = 0; s < C.nstages; ++s) {
                         mbar_wait(bar_ring_full(slot), rphase);
                         tc_fence_after();
@@ -497,27 +520,30 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                         const uint64_t db_hi = make_desc(bs, b_kg, 128);
                         const uint64_t db_lo = make_desc(bs + b_lo, b_kg, 128);
                         const uint32_t acc0 = s > 0 ? 1u : 0u;
-                        if (L.a_src == A_TMEM) {
-                            const uint32_t ta_hi = tm + static_cast<uint32_t>(s * 16);
-                            const uint32_t ta_lo = ta_hi + 8u;
-                            mma_ts(d, ta_hi, db_hi, idesc, acc0);
-                            mma_ts(d, ta_hi, db_lo, idesc, 1u);
-                            mma_ts(d, ta_lo, db_hi, idesc, 1u);
-                        } else {
-                            const uint32_t as = a_base + s * KSTEP_BYTES;
-                            const uint64_t da_hi = make_desc(as, A_KG_BYTES, 128);
-                            const uint64_t da_lo = make_desc(as + 2 * A_KG_BYTES, A_KG_BYTES, 128);
-                            mma_ss(d, da_hi, db_hi, idesc, acc0);
-                            mma_ss(d, da_hi, db_lo, idesc, 1u);
-                            mma_ss(d, da_lo, db_hi, idesc, 1u);
+                        const uint32_t ta_hi = tm + static_cast<uint32_t>(s * 16);
+                        const uint32_t as = a_base + s * KSTEP_BYTES;
+                        const uint64_t da_hi = make_desc(as, A_KG_BYTES, 128);
+                        const uint64_t da_lo = make_desc(as + 2 * A_KG_BYTES, A_KG_BYTES, 128);
+                        if (elect_one()) {
+                            if (ts) {
+                                mma_ts(d, ta_hi, db_hi, idesc, acc0);
+                                mma_ts(d, ta_hi, db_lo, idesc, 1u);
+                                mma_ts(d, ta_hi + 8u, db_hi, idesc, 1u);
+                            } else {
+                                mma_ss(d, da_hi, db_hi, idesc, acc0);
+                                mma_ss(d, da_hi, db_lo, idesc, 1u);
+                                mma_ss(d, da_lo, db_hi, idesc, 1u);
+                            }
+                            mma_commit(bar_ring_empty(slot));  // frees the stage when these MMAs have read it
                         }
-                        mma_commit(bar_ring_empty(slot));  // frees the stage when these MMAs have read it
+                        __syncwarp();
                         if (++slot == P.nslots) {
                             slot = 0;
                             rphase ^= 1u;
                         }
                     }
-                    mma_commit(bar_chunk_full(seq & (NFULL - 1)));
+                    if (elect_one()) mma_commit(bar_chunk_full(seq & (NFULL - 1)));
+                    __syncwarp();
                     ++seq;
                 }
             }
@@ -528,7 +554,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         const int sub = warp & 3;                 // TMEM sub-partition this warp may access
         const int row = sub * 32 + lane;          // tile row == TMEM lane
         const uint32_t tlane = static_cast<uint32_t>(sub * 32) << 16;
-        float* stage = reinterpret_cast<float*>(sm + P.off_act) + (warp - 2) * (32 * 17);
+        float* stage = reinterpret_cast<float*>(sm + P.off_stage) + (warp - 2) * (32 * 17);
         const Layer& LL = P.L[P.n_layers - 1];
         const int NO = P.n_out;
         uint32_t seq = 0;
@@ -577,11 +603,10 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 ++seq;
                 tc_fence_after();
                 const float* bl = s_bias + L.bias_off + C.n0;
-                for (int g = 0; g < C.ncols / 16; ++g) {
-                    uint32_t r[16];
-                    const uint32_t taddr = tm + tlane + static_cast<uint32_t>(C.dcol + 16 * g);
-                    tmem_ld16(taddr, r);
-                    tmem_ld_wait();
+                const int ng = C.ncols / 16;
+                const uint32_t tbase = tm + tlane + static_cast<uint32_t>(C.dcol);
+                auto process = [&](uint32_t (&r)[16], int g) {
+                    const uint32_t taddr = tbase + static_cast<uint32_t>(16 * g);
                     if (L.out_dst != DST_FINAL) {
                         uint32_t w[16];  // [0..7] hi words, [8..15] lo words
 #pragma unroll
@@ -633,6 +658,22 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                                 if (gr < a.n && n + cl < NO) __stcs(a.out + gr * NO + n + cl, stage[rr * 17 + cl]);
                             }
                             __syncwarp();
+                        }
+                    }
+                };
+                // software-pipelined accumulator reads: the load of group g+1 is in flight while group g
+                // is converted
+                {
+                    uint32_t ra[16], rb[16];
+                    tmem_ld16(tbase, ra);
+                    for (int g = 0; g < ng; g += 2) {
+                        tmem_ld_wait();
+                        if (g + 1 < ng) tmem_ld16(tbase + static_cast<uint32_t>(16 * (g + 1)), rb);
+                        process(ra, g);
+                        if (g + 1 < ng) {
+                            tmem_ld_wait();
+                            if (g + 2 < ng) tmem_ld16(tbase + static_cast<uint32_t>(16 * (g + 2)), ra);
+                            process(rb, g + 1);
                         }
                     }
                 }

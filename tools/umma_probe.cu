@@ -193,6 +193,188 @@ probe_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ Bimg, 
     (void)lane;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Timing mode: cycles per tcgen05.mma for a long dependent chain (operand contents irrelevant).
+//   umma_probe t <N> <a_tmem> <layout: 0 none, 2 sw128> <alt_d: 1 = alternate two accumulators> <per_commit>
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+time_kernel(int N, int a_tmem, int layout, int alt_d, int per_commit, int nmma, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < 48 * 1024 / 4; e += 128) reinterpret_cast<uint32_t*>(smem)[e] = 0x3c003c00u + e;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tm = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t sA = smem_u32(smem), sB = smem_u32(smem) + 16384;
+        uint64_t da, db;
+        if (layout == 0) {
+            da = make_desc(sA, 2048, 128);
+            db = make_desc(sB, (uint32_t)N * 16, 128);
+        } else {
+            da = make_desc(sA, 16, 1024) | (2ull << 61);
+            db = make_desc(sB, 16, 1024) | (2ull << 61);
+        }
+        uint32_t parity = 0;
+        const long long t0 = clock64();
+        for (int i = 0; i < nmma; ++i) {
+            const uint32_t d = tm + ((alt_d && (i & 1)) ? 256u : 0u);
+            // walk through a few k-steps worth of operand addresses like the real kernel does
+            const uint32_t step = (uint32_t)(i & 3);
+            const uint64_t dbi = db + (layout == 0 ? (uint64_t)((step * 2 * (uint32_t)N * 16) >> 4) : (uint64_t)((step * 32) >> 4));
+            if (a_tmem) {
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d),
+                             "r"(tm + 480u), "l"(dbi), "r"(idesc), "r"(1u)
+                             : "memory");
+            } else {
+                const uint64_t dai = da + (layout == 0 ? (uint64_t)((step * 4096) >> 4) : (uint64_t)((step * 32) >> 4));
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
+                             "l"(dai), "l"(dbi), "r"(idesc), "r"(1u)
+                             : "memory");
+            }
+            if (per_commit && ((i + 1) % per_commit == 0 || i == nmma - 1)) {
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar)) : "memory");
+                if (i == nmma - 1 || per_commit < 0) {
+                }
+                // only the final commit is waited on; earlier ones just arrive (phase flips are harmless here
+                // because we wait for each in order)
+                mbar_wait(&bar, parity, nullptr, 0);
+                parity ^= 1u;
+            }
+        }
+        if (!per_commit) {
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar)) : "memory");
+            mbar_wait(&bar, 0, nullptr, 0);
+        }
+        const long long t1 = clock64();
+        out[0] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512));
+}
+
+
+// Timing v2: the whole warp runs the (warp-uniform) issue loop, only the MMA itself is predicated on one
+// elected lane (CUTLASS style) so descriptors can live in the uniform datapath.
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %1;\n\tselp.u32 %0, 1, 0, px;\n\t}\n" : "=r"(pred) : "r"(0xffffffffu));
+    return pred;
+}
+template <int UNROLL>
+__global__ void __launch_bounds__(128, 1)
+time_kernel2(int N, int a_tmem, int nmma, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < 48 * 1024 / 4; e += 128) reinterpret_cast<uint32_t*>(smem)[e] = 0x3c003c00u + e;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tm = tmem_base_s;
+    if (warp == 0) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t sA = smem_u32(smem), sB = smem_u32(smem) + 16384;
+        const uint64_t da = make_desc(sA, 2048, 128);
+        const uint64_t db = make_desc(sB, (uint32_t)N * 16, 128);
+        const long long t0 = clock64();
+        for (int i = 0; i < nmma; i += UNROLL) {
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const uint32_t step = (uint32_t)(u & 3);
+                const uint64_t dbi = db + (uint64_t)((step * 2 * (uint32_t)N * 16) >> 4);
+                const uint64_t dai = da + (uint64_t)((step * 4096) >> 4);
+                if (elect_one()) {
+                    if (a_tmem)
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tm),
+                                     "r"(tm + 480u), "l"(dbi), "r"(idesc), "r"(1u) : "memory");
+                    else
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tm),
+                                     "l"(dai), "l"(dbi), "r"(idesc), "r"(1u) : "memory");
+                }
+            }
+        }
+        if (elect_one())
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar)) : "memory");
+        __syncwarp();
+        mbar_wait(&bar, 0, nullptr, 0);
+        const long long t1 = clock64();
+        if ((tid & 31) == 0) out[0] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512));
+}
+
+static int run_timing(int argc, char** argv) {
+    const int N = argc > 2 ? atoi(argv[2]) : 176;
+    const int a_tmem = argc > 3 ? atoi(argv[3]) : 0;
+    const int layout = argc > 4 ? atoi(argv[4]) : 0;
+    const int alt_d = argc > 5 ? atoi(argv[5]) : 0;
+    const int per_commit = argc > 6 ? atoi(argv[6]) : 0;
+    const int nmma = 2048;
+    long long* d;
+    CK(cudaMalloc(&d, 8));
+    cudaFuncSetAttribute(time_kernel2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(time_kernel2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(time_kernel2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (argv[1][1] == '2') {
+        const int unroll = argc > 4 ? atoi(argv[4]) : 1;
+        for (int rep = 0; rep < 2; ++rep) {
+            if (unroll == 1) time_kernel2<1><<<1, 128, 96 * 1024>>>(N, a_tmem, nmma, d);
+            else if (unroll == 4) time_kernel2<4><<<1, 128, 96 * 1024>>>(N, a_tmem, nmma, d);
+            else time_kernel2<8><<<1, 128, 96 * 1024>>>(N, a_tmem, nmma, d);
+            CK(cudaGetLastError());
+            CK(cudaDeviceSynchronize());
+        }
+        long long c2 = 0;
+        CK(cudaMemcpy(&c2, d, 8, cudaMemcpyDeviceToHost));
+        printf("timing2 N=%d a_tmem=%d unroll=%d : %.1f cycles/MMA (floor N/2 = %d)\n", N, a_tmem, unroll, (double)c2 / nmma, N / 2);
+        return 0;
+    }
+    CK(cudaFuncSetAttribute(time_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(time_kernel2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(time_kernel2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(time_kernel2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    for (int rep = 0; rep < 2; ++rep) {
+        time_kernel<<<1, 128, 96 * 1024>>>(N, a_tmem, layout, alt_d, per_commit, nmma, d);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+    }
+    long long cyc = 0;
+    CK(cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost));
+    printf("timing N=%d a_tmem=%d layout=%d alt_d=%d per_commit=%d : %.1f cycles/MMA (floor N/2 = %d)\n", N, a_tmem, layout, alt_d,
+           per_commit, (double)cyc / nmma, N / 2);
+    return 0;
+}
+
 static uint16_t to16(float x, int fp16) {
     if (fp16) {
         __half h = __float2half_rn(x);
@@ -225,6 +407,7 @@ int main(int argc, char** argv) {
         printf("%d\n", nvar);
         return 0;
     }
+    if (argv[1][0] == 't') return run_timing(argc, argv);
     const int vi = atoi(argv[1]);
     if (vi < 0 || vi >= nvar) return 1;
     const Variant v = table[vi];
