@@ -35,7 +35,8 @@
 namespace tck {
 
 constexpr int MT = 128;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;   // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int NEPI = 256;       // epilogue threads
 constexpr int MAXL = 8;
 constexpr int MAXC = 32;
 constexpr int NFULL = 4;          // ring of "accumulator chunk ready" barriers
@@ -209,13 +210,13 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
     // shared memory
     int off = 0;
     P.off_act = off;
-    off += std::max(smem_w / 16 * KSTEP_BYTES, 4 * 32 * 17 * 4);
+    off += std::max(smem_w / 16 * KSTEP_BYTES, 8 * 32 * 20 * 4);
     // The last layer's epilogue transposes through a small staging tile.  It may alias the
     // activation buffer only when the last layer does not read its A operand from there.
     P.off_stage = P.off_act;
     if (P.L[last].a_src == A_SMEM_ACT) {
         P.off_stage = off;
-        off += 4 * 32 * 17 * 4;
+        off += 8 * 32 * 20 * 4;
     }
     P.off_a0 = off;
     off += KSTEP_BYTES;
@@ -229,7 +230,7 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
     P.off_isig = off;
     off += nop * 4;
     P.off_bar = off;
-    off += 256;
+    off += 256 + 2 * 16 * 4 + 2 * 128 * 4;  // barriers + prologue constants + chi^2 partials
     off = (off + 127) / 128 * 128;
     P.off_ring = off;
     const int avail = SMEM_LIMIT - 128 /*alignment slack*/ - off;
@@ -403,6 +404,9 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     const uint32_t bar_act_ready = bar0 + 8u * (2 * MAX_SLOTS + NFULL + 2);
     const uint32_t bar_a0_ready = bar0 + 8u * (2 * MAX_SLOTS + NFULL + 3);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + P.off_bar + 8 * (2 * MAX_SLOTS + NFULL + 4));
+    float* s_pmin = reinterpret_cast<float*>(sm + P.off_bar + 256);   // [16] fp32 copies of the prologue constants
+    float* s_pscale = s_pmin + 16;                                    // [16] 2 / (pmax - pmin)
+    float* s_chi = s_pscale + 16;                                     // [2][128] chi^2 partials of the second column half
 
     float* s_bias = reinterpret_cast<float*>(sm + P.off_bias);
     float* s_s0 = reinterpret_cast<float*>(sm + P.off_s0);
@@ -416,10 +420,14 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             mbar_init(bar_ring_empty(s), 1);
         }
         for (int i = 0; i < NFULL; ++i) mbar_init(bar_chunk_full(i), 1);
-        for (int b = 0; b < 2; ++b) mbar_init(bar_q_empty(b), 128);
-        mbar_init(bar_act_ready, 128);
+        for (int b = 0; b < 2; ++b) mbar_init(bar_q_empty(b), NEPI);
+        mbar_init(bar_act_ready, NEPI);
         mbar_init(bar_a0_ready, 128);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (tid < 16) {
+        s_pmin[tid] = tid < nc.n_par ? static_cast<float>(nc.pmin[tid]) : 0.f;
+        s_pscale[tid] = tid < nc.n_par ? static_cast<float>(2.0 / nc.prange[tid]) : 0.f;
     }
     {
         const Layer& LL = P.L[P.n_layers - 1];
@@ -448,6 +456,8 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     __syncthreads();
     tc_fence_after();
     const uint32_t tm = *tmem_slot;
+    const int n_chunks = P.n_chunks, nslots = P.nslots;
+    const uint32_t ring0 = base + P.off_ring, slot_bytes = static_cast<uint32_t>(P.slot_bytes);
 
     if (warp == 0) {
         // ===================== producer: stream the weight image through the ring ============
@@ -455,19 +465,21 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             int slot = 0;
             uint32_t phase = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int c = 0; c < P.n_chunks; ++c) {
+                for (int c = 0; c < n_chunks; ++c) {
                     const Chunk& C = P.C[c];
                     const uint32_t bytes = static_cast<uint32_t>(C.ncols) * 64u;
                     const uint8_t* src = wimg + C.w_off;
-                    for (int s = 0; s < C.nstages; ++s) {
+                    const int nst = C.nstages;
+                    for (int s = 0; s < nst; ++s) {
                         mbar_wait(bar_ring_empty(slot), phase ^ 1u);
                         mbar_expect_tx(bar_ring_full(slot), bytes);
                         asm volatile(
                             "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                                base + P.off_ring + slot * P.slot_bytes),
-                            "l"(src + static_cast<size_t>(s) * bytes), "r"(bytes), "r"(bar_ring_full(slot))
+                                ring0 + slot * slot_bytes),
+                            "l"(src), "r"(bytes), "r"(bar_ring_full(slot))
                             : "memory");
-                        if (++slot == P.nslots) {
+                        src += bytes;
+                        if (++slot == nslots) {
                             slot = 0;
                             phase ^= 1u;
                         }
@@ -480,87 +492,97 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         // The whole warp runs this (warp-uniform) loop and only the tcgen05 instructions are
         // predicated on one elected lane: measured with tools/umma_probe.cu, a loop inside an
         // `if (lane == 0)` branch costs 269 cycles per MMA, this form 96..131.
-        {
-            int slot = 0;
-            uint32_t rphase = 0;
-            uint32_t seq = 0;                 // running chunk counter (chunk_full ring)
-            uint32_t q_use0 = 0, q_use1 = 0;  // uses so far of each ring accumulator
-            uint32_t act_cnt = 0, a0_cnt = 0;
-            const uint32_t fmtbits = (FMT == 0) ? 1u : 0u;
-            const uint32_t idesc_base = (1u << 4) | (fmtbits << 7) | (fmtbits << 10) | ((128u >> 4) << 24);
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int c = 0; c < P.n_chunks; ++c) {
-                    const Chunk& C = P.C[c];
-                    const Layer& L = P.L[C.layer];
-                    if (c == L.first_chunk) {  // this layer's A operand must be complete
-                        if (C.layer == 0) {
-                            mbar_wait(bar_a0_ready, a0_cnt & 1u);
-                            ++a0_cnt;
-                        } else {
-                            mbar_wait(bar_act_ready, act_cnt & 1u);
-                            ++act_cnt;
-                        }
+        int slot = 0;
+        uint32_t rphase = 0;
+        uint32_t seq = 0;                 // running chunk counter (chunk_full ring)
+        uint32_t q_use0 = 0, q_use1 = 0;  // uses so far of each ring accumulator
+        uint32_t act_cnt = 0, a0_cnt = 0;
+        const uint32_t fmtbits = (FMT == 0) ? 1u : 0u;
+        const uint32_t idesc_base = (1u << 4) | (fmtbits << 7) | (fmtbits << 10) | ((128u >> 4) << 24);
+        // descriptor high words are constant: SBO = 128 B, version 1; LBO goes into the low word
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+        const uint32_t a_lbo = (static_cast<uint32_t>(A_KG_BYTES) >> 4) << 16;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int c = 0; c < n_chunks; ++c) {
+                const Chunk& C = P.C[c];
+                const Layer& L = P.L[C.layer];
+                if (c == L.first_chunk) {  // this layer's A operand must be complete
+                    if (C.layer == 0) {
+                        mbar_wait(bar_a0_ready, a0_cnt & 1u);
+                        ++a0_cnt;
+                    } else {
+                        mbar_wait(bar_act_ready, act_cnt & 1u);
+                        ++act_cnt;
                     }
-                    if (C.qbuf >= 0) {  // accumulator buffer must have been drained by the epilogue
-                        const uint32_t u = C.qbuf ? q_use1 : q_use0;
-                        if (C.qbuf) ++q_use1; else ++q_use0;
-                        if (u > 0) mbar_wait(bar_q_empty(C.qbuf), (u - 1u) & 1u);
-                    }
-                    tc_fence_after();
-                    const uint32_t idesc = idesc_base | (static_cast<uint32_t>(C.ncols >> 3) << 17);
-                    const uint32_t d = tm + static_cast<uint32_t>(C.dcol);
-                    const uint32_t b_kg = static_cast<uint32_t>(C.ncols) * 16u;  // bytes between B k-groups
-                    const uint32_t b_lo = b_kg * 2u;                             // hi tile -> lo tile
-                    const uint32_t a_base = base + (L.a_src == A_SMEM_A0 ? P.off_a0 : P.off_act);
-                    const bool ts = (L.a_src == A_TMEM);
-                    for (int s = 0; s < C.nstages; ++s) {
-                        mbar_wait(bar_ring_full(slot), rphase);
-                        tc_fence_after();
-                        const uint32_t bs = base + P.off_ring + slot * P.slot_bytes;
-                        const uint64_t db_hi = make_desc(bs, b_kg, 128);
-                        const uint64_t db_lo = make_desc(bs + b_lo, b_kg, 128);
-                        const uint32_t acc0 = s > 0 ? 1u : 0u;
-                        const uint32_t ta_hi = tm + static_cast<uint32_t>(s * 16);
-                        const uint32_t as = a_base + s * KSTEP_BYTES;
-                        const uint64_t da_hi = make_desc(as, A_KG_BYTES, 128);
-                        const uint64_t da_lo = make_desc(as + 2 * A_KG_BYTES, A_KG_BYTES, 128);
-                        if (elect_one()) {
-                            if (ts) {
-                                mma_ts(d, ta_hi, db_hi, idesc, acc0);
-                                mma_ts(d, ta_hi, db_lo, idesc, 1u);
-                                mma_ts(d, ta_hi + 8u, db_hi, idesc, 1u);
-                            } else {
-                                mma_ss(d, da_hi, db_hi, idesc, acc0);
-                                mma_ss(d, da_hi, db_lo, idesc, 1u);
-                                mma_ss(d, da_lo, db_hi, idesc, 1u);
-                            }
-                            mma_commit(bar_ring_empty(slot));  // frees the stage when these MMAs have read it
-                        }
-                        __syncwarp();
-                        if (++slot == P.nslots) {
-                            slot = 0;
-                            rphase ^= 1u;
-                        }
-                    }
-                    if (elect_one()) mma_commit(bar_chunk_full(seq & (NFULL - 1)));
-                    __syncwarp();
-                    ++seq;
                 }
+                if (C.qbuf >= 0) {  // accumulator buffer must have been drained by the epilogue
+                    const uint32_t u = C.qbuf ? q_use1 : q_use0;
+                    if (C.qbuf) ++q_use1; else ++q_use0;
+                    if (u > 0) mbar_wait(bar_q_empty(C.qbuf), (u - 1u) & 1u);
+                }
+                tc_fence_after();
+                const uint32_t idesc = idesc_base | (static_cast<uint32_t>(C.ncols >> 3) << 17);
+                const uint32_t d = tm + static_cast<uint32_t>(C.dcol);
+                const uint32_t b_kg = static_cast<uint32_t>(C.ncols) * 16u;   // bytes between B k-groups
+                const uint32_t b_lbo = (b_kg >> 4) << 16;
+                const uint32_t b_lo16 = (b_kg * 2u) >> 4;                     // hi tile -> lo tile, in 16 B units
+                const bool ts = (L.a_src == A_TMEM);
+                uint32_t a_lo32 = (((base + (L.a_src == A_SMEM_A0 ? P.off_a0 : P.off_act)) & 0x3FFFFu) >> 4) | a_lbo;
+                uint32_t ta = tm;
+                const int nst = C.nstages;
+                for (int s = 0; s < nst; ++s) {
+                    mbar_wait(bar_ring_full(slot), rphase);
+                    tc_fence_after();
+                    const uint32_t b_lo32 = (((ring0 + slot * slot_bytes) & 0x3FFFFu) >> 4) | b_lbo;
+                    const uint64_t db_hi = (static_cast<uint64_t>(desc_hi) << 32) | b_lo32;
+                    const uint64_t db_lo = db_hi + b_lo16;
+                    const uint32_t acc0 = s > 0 ? 1u : 0u;
+                    if (elect_one()) {
+                        if (ts) {
+                            mma_ts(d, ta, db_hi, idesc, acc0);
+                            mma_ts(d, ta, db_lo, idesc, 1u);
+                            mma_ts(d, ta + 8u, db_hi, idesc, 1u);
+                        } else {
+                            const uint64_t da_hi = (static_cast<uint64_t>(desc_hi) << 32) | a_lo32;
+                            const uint64_t da_lo = da_hi + ((2u * A_KG_BYTES) >> 4);
+                            mma_ss(d, da_hi, db_hi, idesc, acc0);
+                            mma_ss(d, da_hi, db_lo, idesc, 1u);
+                            mma_ss(d, da_lo, db_hi, idesc, 1u);
+                        }
+                        mma_commit(bar_ring_empty(slot));  // frees the stage when these MMAs have read it
+                    }
+                    __syncwarp();
+                    a_lo32 += KSTEP_BYTES >> 4;
+                    ta += 16u;
+                    if (++slot == nslots) {
+                        slot = 0;
+                        rphase ^= 1u;
+                    }
+                }
+                if (elect_one()) mma_commit(bar_chunk_full(seq & (NFULL - 1)));
+                __syncwarp();
+                ++seq;
             }
         }
         __syncwarp();
     } else {
-        // ===================== epilogue warps (thread = row) ==================================
+        // ===================== epilogue warps ================================================
+        // thread = tile row = TMEM lane; the two warps that share a TMEM sub-partition split the
+        // 16-column groups of every accumulator chunk (even / odd groups).
+        const int ew = warp - 2;
+        const int half = ew >> 2;                 // 0: even groups (+ the prologue), 1: odd groups
         const int sub = warp & 3;                 // TMEM sub-partition this warp may access
         const int row = sub * 32 + lane;          // tile row == TMEM lane
         const uint32_t tlane = static_cast<uint32_t>(sub * 32) << 16;
-        float* stage = reinterpret_cast<float*>(sm + P.off_stage) + (warp - 2) * (32 * 17);
-        const Layer& LL = P.L[P.n_layers - 1];
+        float* stage = reinterpret_cast<float*>(sm + P.off_stage) + ew * (32 * 20);
         const int NO = P.n_out;
+        const int K0 = P.K0;
         uint32_t seq = 0;
+        uint32_t tcount = 0;
 
         auto write_a0 = [&](long long tile) {
-            // fused parameter transform (preprocess.py:74-78, :105-108) -> layer-0 operand (k padded to 16)
+            // fused parameter transform (preprocess.py:74-78, :105-108) in fp32 -- the operand is
+            // split to 16-bit hi/lo pairs anyway -- -> layer-0 operand (k padded to 16)
             const long long grow = tile * MT + row;
             float x[16];
 #pragma unroll
@@ -568,14 +590,24 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             if (grow < a.n) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    if (j < P.K0) {
-                        const long long g = grow * P.K0 + j;
-                        if (a.in_mode == IN_PARAMS_F64)
-                            x[j] = transform_param(reinterpret_cast<const double*>(a.in)[g], j, nc, false);
-                        else if (a.in_mode == IN_PARAMS_F32)
-                            x[j] = transform_param(static_cast<double>(reinterpret_cast<const float*>(a.in)[g]), j, nc, true);
-                        else
+                    if (j < K0) {
+                        const long long g = grow * K0 + j;
+                        if (a.in_mode == IN_NORMALISED_F32) {
                             x[j] = reinterpret_cast<const float*>(a.in)[g];
+                        } else {
+                            const double pd = (a.in_mode == IN_PARAMS_F64)
+                                                  ? reinterpret_cast<const double*>(a.in)[g]
+                                                  : static_cast<double>(reinterpret_cast<const float*>(a.in)[g]);
+                            float pf = static_cast<float>(pd);
+                            if (j == nc.floor_col && pd == 0.0) pf = static_cast<float>(nc.floor_val);
+                            float t = pf;
+                            if (nc.log_mask[j]) {
+                                t = log10f(pf);
+                                // a finite non-zero double outside the float range: take the slow exact route
+                                if ((pf == 0.f || isinf(pf)) && pd != 0.0 && !isinf(pd)) t = static_cast<float>(log10(pd));
+                            }
+                            x[j] = fmaf(t - s_pmin[j], s_pscale[j], -1.f);
+                        }
                     }
                 }
             }
@@ -591,12 +623,17 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             mbar_arrive(bar_a0_ready);
         };
 
-        if (static_cast<long long>(blockIdx.x) < ntiles) write_a0(blockIdx.x);
+        if (half == 0 && static_cast<long long>(blockIdx.x) < ntiles) write_a0(blockIdx.x);
 
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
             const long long grow = tile * MT + row;
+            const bool full_tile = (tile * MT + MT <= a.n);
+            // output pointer of (row 32*sub + lane/16, column lane%16): each store instruction of the final layer
+            // writes two 64-byte row segments
+            const int cl = lane & 15, rsel = lane >> 4;
+            float* orow = a.out + (tile * MT + sub * 32 + rsel) * static_cast<long long>(NO) + cl;
             float chi = 0.f;
-            for (int c = 0; c < P.n_chunks; ++c) {
+            for (int c = 0; c < n_chunks; ++c) {
                 const Chunk& C = P.C[c];
                 const Layer& L = P.L[C.layer];
                 mbar_wait(bar_chunk_full(seq & (NFULL - 1)), (seq / NFULL) & 1u);
@@ -605,9 +642,11 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 const float* bl = s_bias + L.bias_off + C.n0;
                 const int ng = C.ncols / 16;
                 const uint32_t tbase = tm + tlane + static_cast<uint32_t>(C.dcol);
+                const int out_dst = L.out_dst;
+                const bool do_relu = L.relu != 0;
                 auto process = [&](uint32_t (&r)[16], int g) {
                     const uint32_t taddr = tbase + static_cast<uint32_t>(16 * g);
-                    if (L.out_dst != DST_FINAL) {
+                    if (out_dst != DST_FINAL) {
                         uint32_t w[16];  // [0..7] hi words, [8..15] lo words
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -616,7 +655,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                             float v1 = __uint_as_float(r[4 * q + 1]) + b4.y;
                             float v2 = __uint_as_float(r[4 * q + 2]) + b4.z;
                             float v3 = __uint_as_float(r[4 * q + 3]) + b4.w;
-                            if (L.relu) {
+                            if (do_relu) {
                                 v0 = relu_nan(v0);
                                 v1 = relu_nan(v1);
                                 v2 = relu_nan(v2);
@@ -625,7 +664,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                             split2<FMT>(v0, v1, w[2 * q], w[8 + 2 * q]);
                             split2<FMT>(v2, v3, w[2 * q + 1], w[8 + 2 * q + 1]);
                         }
-                        if (L.out_dst == DST_TMEM) {
+                        if (out_dst == DST_TMEM) {
                             tmem_st16(taddr, w);  // in place: these 16 columns become the next layer's k-step
                         } else {
                             uint8_t* dst = sm + P.off_act + ((C.n0 >> 4) + g) * KSTEP_BYTES + row * 16;
@@ -637,59 +676,81 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                     } else {
                         const int n = C.n0 + 16 * g;
                         const float s1 = (a.out_mode == OUT_NORMALISED) ? 1.f : nc.sd;
+                        float v[16];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 s4 = *reinterpret_cast<const float4*>(s_s0 + n + 4 * q);
+                            v[4 * q + 0] = fmaf(__uint_as_float(r[4 * q + 0]), s1, s4.x);
+                            v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), s1, s4.y);
+                            v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), s1, s4.z);
+                            v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), s1, s4.w);
+                        }
                         if (a.out_mode == OUT_CHI2) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
-                                const float v = fmaf(__uint_as_float(r[i]), s1, s_s0[n + i]);
-                                const float rr = (v - s_obs[n + i]) * s_isig[n + i];  // isig = 0 on padding
+                                const float rr = (v[i] - s_obs[n + i]) * s_isig[n + i];  // isig = 0 on padding
                                 chi = fmaf(rr, rr, chi);
                             }
                         } else {
-                            // 32x16 transpose through this warp's staging tile -> coalesced row segments
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) stage[lane * 17 + i] = fmaf(__uint_as_float(r[i]), s1, s_s0[n + i]);
+                            // 32x16 transpose through this warp's staging tile (row stride 20 floats: conflict-free
+                            // 128-bit writes) -> every store instruction writes two 64-byte row segments
+                            float4* st4 = reinterpret_cast<float4*>(stage + lane * 20);
+                            st4[0] = make_float4(v[0], v[1], v[2], v[3]);
+                            st4[1] = make_float4(v[4], v[5], v[6], v[7]);
+                            st4[2] = make_float4(v[8], v[9], v[10], v[11]);
+                            st4[3] = make_float4(v[12], v[13], v[14], v[15]);
                             __syncwarp();
-                            const int cl = lane & 15, rsel = lane >> 4;
-                            const long long rbase = tile * MT + sub * 32;
+                            const float* sp = stage + rsel * 20 + cl;
+                            float* op = orow + n;
+                            if (full_tile && n + 16 <= NO) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const int rr = 2 * i + rsel;
-                                const long long gr = rbase + rr;
-                                if (gr < a.n && n + cl < NO) __stcs(a.out + gr * NO + n + cl, stage[rr * 17 + cl]);
+                                for (int i = 0; i < 16; ++i) __stcs(op + static_cast<long long>(2 * i) * NO, sp[2 * i * 20]);
+                            } else {
+                                const long long rbase = tile * MT + sub * 32 + rsel;
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (rbase + 2 * i < a.n && n + cl < NO) __stcs(op + static_cast<long long>(2 * i) * NO, sp[2 * i * 20]);
                             }
                             __syncwarp();
                         }
                     }
                 };
-                // software-pipelined accumulator reads: the load of group g+1 is in flight while group g
-                // is converted
-                {
+                // software-pipelined accumulator reads: the load of this warp's next group is in flight while
+                // the current one is converted
+                if (half < ng) {
                     uint32_t ra[16], rb[16];
-                    tmem_ld16(tbase, ra);
-                    for (int g = 0; g < ng; g += 2) {
+                    tmem_ld16(tbase + static_cast<uint32_t>(16 * half), ra);
+                    for (int g = half; g < ng; g += 4) {
                         tmem_ld_wait();
-                        if (g + 1 < ng) tmem_ld16(tbase + static_cast<uint32_t>(16 * (g + 1)), rb);
+                        if (g + 2 < ng) tmem_ld16(tbase + static_cast<uint32_t>(16 * (g + 2)), rb);
                         process(ra, g);
-                        if (g + 1 < ng) {
+                        if (g + 2 < ng) {
                             tmem_ld_wait();
-                            if (g + 2 < ng) tmem_ld16(tbase + static_cast<uint32_t>(16 * (g + 2)), ra);
-                            process(rb, g + 1);
+                            if (g + 4 < ng) tmem_ld16(tbase + static_cast<uint32_t>(16 * (g + 4)), ra);
+                            process(rb, g + 2);
                         }
                     }
                 }
                 // publish: operand visible to the tensor pipe / accumulator buffer free
-                if (L.out_dst == DST_SMEM) fence_async_smem();
-                if (L.out_dst == DST_TMEM) tmem_st_wait();
+                if (out_dst == DST_SMEM) fence_async_smem();
+                if (out_dst == DST_TMEM) tmem_st_wait();
                 tc_fence_before();
                 if (C.qbuf >= 0) mbar_arrive(bar_q_empty(C.qbuf));
-                if (L.out_dst != DST_FINAL && c == L.first_chunk + L.nchunks - 1) mbar_arrive(bar_act_ready);
+                const bool last_of_layer = (c == L.first_chunk + L.nchunks - 1);
+                if (out_dst != DST_FINAL && last_of_layer) mbar_arrive(bar_act_ready);
                 // the layer-0 operand of the NEXT tile can be written as soon as layer 0 of this tile is done
-                if (C.layer == 0 && c == L.first_chunk + L.nchunks - 1) {
+                if (half == 0 && C.layer == 0 && last_of_layer) {
                     const long long nt = tile + gridDim.x;
                     if (nt < ntiles) write_a0(nt);
                 }
             }
-            if (a.out_mode == OUT_CHI2) {
+            // tile end: all epilogue warps meet (the output staging tiles alias the activation buffer, and the
+            // two column halves of a row combine their chi^2 partials here)
+            float* chi_buf = s_chi + (tcount & 1u) * 128;
+            if (a.out_mode == OUT_CHI2 && half == 1) chi_buf[row] = chi;
+            asm volatile("bar.sync 1, %0;\n" ::"n"(NEPI) : "memory");
+            if (a.out_mode == OUT_CHI2 && half == 0) {
+                chi += chi_buf[row];
                 unsigned long long key = ~0ull;
                 if (grow < a.n) {
                     if (a.chi2) a.chi2[grow] = chi;
@@ -704,10 +765,6 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                     if (lane == 0 && key != ~0ull) atomicMin(a.argmin_key, key);
                 }
             }
-            (void)LL;
-            // the output staging tiles alias the activation buffer: no warp may start writing the next
-            // tile's activations before every epilogue warp is done with its staging tile
-            asm volatile("bar.sync 1, 128;\n" ::: "memory");
         }
     }
 
