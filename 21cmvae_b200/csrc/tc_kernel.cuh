@@ -26,6 +26,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -73,6 +74,7 @@ struct Plan {
     int K0;      // true number of input parameters
     int n_out;   // true output width
     int slot_bytes, nslots;
+    int lookahead;  // MMA warp polls the weight ring two stages ahead
     int bias_total;
     // shared-memory carve-up (bytes from the 1024-aligned base)
     int off_act, off_stage, off_a0, off_ring, off_bias, off_s0, off_obs, off_isig, off_bar, smem_total;
@@ -117,6 +119,7 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
     if (relu[n_layers - 1]) { why = "last layer must be linear"; return false; }
     if (dims[0] > 16) { why = "more than 16 input parameters"; return false; }
     P.n_layers = n_layers;
+    P.lookahead = std::getenv("VAE21_TC_LOOKAHEAD") ? 1 : 0;  // measured slower (2.87 vs 2.72 ms): off by default
     P.K0 = dims[0];
     P.n_out = dims[n_layers];
     auto pad16 = [](int x) { return (x + 15) / 16 * 16; };
@@ -129,8 +132,26 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
         L.N = dims[l + 1];
         L.Npad = pad16(L.N);
         L.relu = relu[l] ? 1 : 0;
-        L.a_src = (l == 0) ? A_SMEM_A0 : ((l & 1) ? A_SMEM_ACT : A_TMEM);
-        L.out_dst = (l == n_layers - 1) ? DST_FINAL : ((l & 1) ? DST_TMEM : DST_SMEM);
+        // Operand placement.  Activations alternate between shared memory (UMMA "SS") and TMEM (converted in
+        // place over the accumulator, UMMA "TS").  A layer that reads shared memory and fits ONE accumulator
+        // chunk may also write shared memory (its epilogue starts after all its MMAs have read the input),
+        // which leaves all of TMEM to the next layer's accumulators: fewer, wider MMAs.  Measured on the
+        // DirectEmulator stack this is SLOWER (2.72 vs 2.52 ms per 1M rows: the wide last chunk's epilogue
+        // delays the next tile), so it is opt-in (VAE21_TC_SS_LAST=1).
+        if (l == 0) {
+            L.a_src = A_SMEM_A0;
+        } else {
+            L.a_src = (P.L[l - 1].out_dst == DST_SMEM) ? A_SMEM_ACT : A_TMEM;
+        }
+        if (l == n_layers - 1) {
+            L.out_dst = DST_FINAL;
+        } else if (L.a_src == A_SMEM_A0) {
+            L.out_dst = DST_SMEM;
+        } else if (L.a_src == A_SMEM_ACT) {
+            L.out_dst = (L.Npad <= 224 && l == n_layers - 2 && std::getenv("VAE21_TC_SS_LAST")) ? DST_SMEM : DST_TMEM;
+        } else {
+            L.out_dst = DST_SMEM;
+        }
         L.bias_off = boff;
         boff += L.Npad;
         if (L.out_dst == DST_SMEM) smem_w = std::max(smem_w, L.Npad);
@@ -172,7 +193,7 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
             // layer 0 shares the ring geometry of the last layer (their accumulators overlap in
             // time across consecutive tiles without a drain in between)
             qgeom(l == 0 ? last : l, q0, qsize, nbuf);
-            maxcols = std::min(qsize, 224);
+            maxcols = std::min(qsize, 240);
             if (maxcols < 16) { why = "no TMEM left for accumulators"; return false; }
         }
         const int nch = (L.Npad + maxcols - 1) / maxcols;
@@ -210,14 +231,18 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
     // shared memory
     int off = 0;
     P.off_act = off;
-    off += std::max(smem_w / 16 * KSTEP_BYTES, 8 * 32 * 20 * 4);
-    // The last layer's epilogue transposes through a small staging tile.  It may alias the
-    // activation buffer only when the last layer does not read its A operand from there.
-    P.off_stage = P.off_act;
+    const int stage_bytes = 8 * 32 * 20 * 4;  // output transpose staging of the 8 epilogue warps
+    int act_bytes = std::max(smem_w / 16 * KSTEP_BYTES, stage_bytes);
+    // The staging tiles alias the activation buffer where the last layer does not read it: all of it when
+    // the last layer's operand is in TMEM, else the part above that operand (grown if needed).
     if (P.L[last].a_src == A_SMEM_ACT) {
+        const int used = P.L[last].K / 16 * KSTEP_BYTES;
+        act_bytes = std::max(act_bytes, used + stage_bytes);
+        P.off_stage = off + used;
+    } else {
         P.off_stage = off;
-        off += 8 * 32 * 20 * 4;
     }
+    off += act_bytes;
     P.off_a0 = off;
     off += KSTEP_BYTES;
     P.off_bias = off;
@@ -311,6 +336,17 @@ __device__ __forceinline__ uint32_t elect_one() {
                  : "=r"(pred)
                  : "r"(0xffffffffu));
     return pred;
+}
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -497,6 +533,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         uint32_t seq = 0;                 // running chunk counter (chunk_full ring)
         uint32_t q_use0 = 0, q_use1 = 0;  // uses so far of each ring accumulator
         uint32_t act_cnt = 0, a0_cnt = 0;
+        uint32_t look1 = 0, look2 = 0;    // results of the ring probes issued one / two stages ago
         const uint32_t fmtbits = (FMT == 0) ? 1u : 0u;
         const uint32_t idesc_base = (1u << 4) | (fmtbits << 7) | (fmtbits << 10) | ((128u >> 4) << 24);
         // descriptor high words are constant: SBO = 128 B, version 1; LBO goes into the low word
@@ -531,7 +568,20 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 uint32_t ta = tm;
                 const int nst = C.nstages;
                 for (int s = 0; s < nst; ++s) {
-                    mbar_wait(bar_ring_full(slot), rphase);
+                    // look-ahead polling: the test of the stage two ahead was issued two iterations ago, so the
+                    // ~90-cycle latency of the barrier probe is off the issue path when the data is already there
+                    const uint32_t ready = look1;
+                    look1 = look2;
+                    {
+                        int s2 = slot + 2;
+                        uint32_t p2 = rphase;
+                        if (s2 >= nslots) {
+                            s2 -= nslots;
+                            p2 ^= 1u;
+                        }
+                        look2 = P.lookahead ? mbar_test(bar_ring_full(s2), p2) : 0u;
+                    }
+                    if (!ready) mbar_wait(bar_ring_full(slot), rphase);
                     tc_fence_after();
                     const uint32_t b_lo32 = (((ring0 + slot * slot_bytes) & 0x3FFFFu) >> 4) | b_lbo;
                     const uint64_t db_hi = (static_cast<uint64_t>(desc_hi) << 32) | b_lo32;
