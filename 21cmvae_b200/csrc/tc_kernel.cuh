@@ -42,6 +42,7 @@ constexpr int MAXL = 8;
 constexpr int MAXC = 32;
 constexpr int NFULL = 4;          // ring of "accumulator chunk ready" barriers
 constexpr int MAX_SLOTS = 8;
+constexpr int MAX_LCHUNK = 4;      // chunks per non-final layer (per-chunk operand-ready barriers)
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int KSTEP_BYTES = 8192; // one k-step (16 features) of a 128-row activation tile: hi 4 KB + lo 4 KB
 constexpr int A_KG_BYTES = 2048;  // 128 rows x 16 B: distance between the two k-groups of a k-step
@@ -221,6 +222,7 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
             ++nchunks;
         }
         L.nchunks = nch;
+        if (l < n_layers - 1 && nch > MAX_LCHUNK) { why = "too many chunks in a hidden layer"; return false; }
     }
     // every tile must use each ring buffer an even... no: parity is tracked with running counters.
     P.n_chunks = nchunks;
@@ -337,6 +339,17 @@ __device__ __forceinline__ uint32_t elect_one() {
                  : "r"(0xffffffffu));
     return pred;
 }
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
 __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -437,9 +450,9 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     auto bar_ring_empty = [&](int s) { return bar0 + 8u * (MAX_SLOTS + s); };
     auto bar_chunk_full = [&](int i) { return bar0 + 8u * (2 * MAX_SLOTS + i); };
     auto bar_q_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + NFULL + b); };
-    const uint32_t bar_act_ready = bar0 + 8u * (2 * MAX_SLOTS + NFULL + 2);
-    const uint32_t bar_a0_ready = bar0 + 8u * (2 * MAX_SLOTS + NFULL + 3);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + P.off_bar + 8 * (2 * MAX_SLOTS + NFULL + 4));
+    auto bar_act_ready = [&](int j) { return bar0 + 8u * (2 * MAX_SLOTS + NFULL + 2 + j); };  // j < MAX_LCHUNK
+    const uint32_t bar_a0_ready = bar0 + 8u * (2 * MAX_SLOTS + NFULL + 2 + MAX_LCHUNK);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + P.off_bar + 8 * (2 * MAX_SLOTS + NFULL + 3 + MAX_LCHUNK));
     float* s_pmin = reinterpret_cast<float*>(sm + P.off_bar + 256);   // [16] fp32 copies of the prologue constants
     float* s_pscale = s_pmin + 16;                                    // [16] 2 / (pmax - pmin)
     float* s_chi = s_pscale + 16;                                     // [2][128] chi^2 partials of the second column half
@@ -457,7 +470,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         }
         for (int i = 0; i < NFULL; ++i) mbar_init(bar_chunk_full(i), 1);
         for (int b = 0; b < 2; ++b) mbar_init(bar_q_empty(b), NEPI);
-        mbar_init(bar_act_ready, NEPI);
+        for (int j = 0; j < MAX_LCHUNK; ++j) mbar_init(bar_act_ready(j), NEPI);
         mbar_init(bar_a0_ready, 128);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -532,8 +545,8 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         uint32_t rphase = 0;
         uint32_t seq = 0;                 // running chunk counter (chunk_full ring)
         uint32_t q_use0 = 0, q_use1 = 0;  // uses so far of each ring accumulator
-        uint32_t act_cnt = 0, a0_cnt = 0;
-        uint32_t look1 = 0, look2 = 0;    // results of the ring probes issued one / two stages ago
+        uint32_t act_cnt[MAX_LCHUNK] = {0, 0, 0, 0};
+        uint32_t a0_cnt = 0;
         const uint32_t fmtbits = (FMT == 0) ? 1u : 0u;
         const uint32_t idesc_base = (1u << 4) | (fmtbits << 7) | (fmtbits << 10) | ((128u >> 4) << 24);
         // descriptor high words are constant: SBO = 128 B, version 1; LBO goes into the low word
@@ -543,13 +556,17 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             for (int c = 0; c < n_chunks; ++c) {
                 const Chunk& C = P.C[c];
                 const Layer& L = P.L[C.layer];
-                if (c == L.first_chunk) {  // this layer's A operand must be complete
+                // Operand readiness is tracked per chunk of the PRODUCING layer: k-step s of this layer only needs
+                // the 16 features [16 s, 16 s + 16), so the first chunk of a layer starts as soon as the first chunk of
+                // the previous layer has been converted and waits for the later ones when it reaches their k range.
+                int src = -1, src_end = -1;  // chunks of the producing layer still to wait for
+                if (c == L.first_chunk) {
                     if (C.layer == 0) {
                         mbar_wait(bar_a0_ready, a0_cnt & 1u);
                         ++a0_cnt;
                     } else {
-                        mbar_wait(bar_act_ready, act_cnt & 1u);
-                        ++act_cnt;
+                        src = P.L[C.layer - 1].first_chunk;
+                        src_end = src + P.L[C.layer - 1].nchunks;
                     }
                 }
                 if (C.qbuf >= 0) {  // accumulator buffer must have been drained by the epilogue
@@ -567,45 +584,72 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 uint32_t a_lo32 = (((base + (L.a_src == A_SMEM_A0 ? P.off_a0 : P.off_act)) & 0x3FFFFu) >> 4) | a_lbo;
                 uint32_t ta = tm;
                 const int nst = C.nstages;
-                for (int s = 0; s < nst; ++s) {
-                    // look-ahead polling: the test of the stage two ahead was issued two iterations ago, so the
-                    // ~90-cycle latency of the barrier probe is off the issue path when the data is already there
-                    const uint32_t ready = look1;
-                    look1 = look2;
-                    {
-                        int s2 = slot + 2;
-                        uint32_t p2 = rphase;
-                        if (s2 >= nslots) {
-                            s2 -= nslots;
-                            p2 ^= 1u;
-                        }
-                        look2 = P.lookahead ? mbar_test(bar_ring_full(s2), p2) : 0u;
+                int next_src_k = (src >= 0) ? 0 : 0x7fffffff;  // k-step at which the next producing chunk starts
+                for (int s = 0; s < nst; s += 2) {
+                    const bool two = (s + 1 < nst);
+                    // k-steps s (and s+1) may cross into the next chunk of the producing layer
+                    while (s + (two ? 1 : 0) >= next_src_k) {
+                        const int j = src - P.L[C.layer - 1].first_chunk;
+                        mbar_wait(bar_act_ready(j), (act_cnt[j]++) & 1u);
+                        ++src;
+                        next_src_k = (src < src_end) ? (P.C[src].n0 >> 4) : 0x7fffffff;
+                        tc_fence_after();
                     }
-                    if (!ready) mbar_wait(bar_ring_full(slot), rphase);
+                    // probe both stages' barriers back to back (their ~90-cycle latencies overlap)
+                    int slot1 = slot + 1;
+                    uint32_t ph1 = rphase;
+                    if (slot1 == nslots) {
+                        slot1 = 0;
+                        ph1 ^= 1u;
+                    }
+                    const uint32_t ok0 = mbar_try(bar_ring_full(slot), rphase);
+                    const uint32_t ok1 = two ? mbar_try(bar_ring_full(slot1), ph1) : 1u;
+                    if (!ok0) mbar_wait(bar_ring_full(slot), rphase);
+                    if (!ok1) mbar_wait(bar_ring_full(slot1), ph1);
                     tc_fence_after();
-                    const uint32_t b_lo32 = (((ring0 + slot * slot_bytes) & 0x3FFFFu) >> 4) | b_lbo;
-                    const uint64_t db_hi = (static_cast<uint64_t>(desc_hi) << 32) | b_lo32;
-                    const uint64_t db_lo = db_hi + b_lo16;
+                    const uint32_t b0_lo32 = (((ring0 + slot * slot_bytes) & 0x3FFFFu) >> 4) | b_lbo;
+                    const uint32_t b1_lo32 = (((ring0 + slot1 * slot_bytes) & 0x3FFFFu) >> 4) | b_lbo;
+                    const uint64_t db0_hi = (static_cast<uint64_t>(desc_hi) << 32) | b0_lo32;
+                    const uint64_t db0_lo = db0_hi + b_lo16;
+                    const uint64_t db1_hi = (static_cast<uint64_t>(desc_hi) << 32) | b1_lo32;
+                    const uint64_t db1_lo = db1_hi + b_lo16;
                     const uint32_t acc0 = s > 0 ? 1u : 0u;
                     if (elect_one()) {
                         if (ts) {
-                            mma_ts(d, ta, db_hi, idesc, acc0);
-                            mma_ts(d, ta, db_lo, idesc, 1u);
-                            mma_ts(d, ta + 8u, db_hi, idesc, 1u);
+                            mma_ts(d, ta, db0_hi, idesc, acc0);
+                            mma_ts(d, ta, db0_lo, idesc, 1u);
+                            mma_ts(d, ta + 8u, db0_hi, idesc, 1u);
+                            mma_commit(bar_ring_empty(slot));  // frees the stage when these MMAs have read it
+                            if (two) {
+                                mma_ts(d, ta + 16u, db1_hi, idesc, 1u);
+                                mma_ts(d, ta + 16u, db1_lo, idesc, 1u);
+                                mma_ts(d, ta + 24u, db1_hi, idesc, 1u);
+                                mma_commit(bar_ring_empty(slot1));
+                            }
                         } else {
                             const uint64_t da_hi = (static_cast<uint64_t>(desc_hi) << 32) | a_lo32;
                             const uint64_t da_lo = da_hi + ((2u * A_KG_BYTES) >> 4);
-                            mma_ss(d, da_hi, db_hi, idesc, acc0);
-                            mma_ss(d, da_hi, db_lo, idesc, 1u);
-                            mma_ss(d, da_lo, db_hi, idesc, 1u);
+                            mma_ss(d, da_hi, db0_hi, idesc, acc0);
+                            mma_ss(d, da_hi, db0_lo, idesc, 1u);
+                            mma_ss(d, da_lo, db0_hi, idesc, 1u);
+                            mma_commit(bar_ring_empty(slot));
+                            if (two) {
+                                const uint64_t da1_hi = da_hi + (KSTEP_BYTES >> 4);
+                                const uint64_t da1_lo = da_lo + (KSTEP_BYTES >> 4);
+                                mma_ss(d, da1_hi, db1_hi, idesc, 1u);
+                                mma_ss(d, da1_hi, db1_lo, idesc, 1u);
+                                mma_ss(d, da1_lo, db1_hi, idesc, 1u);
+                                mma_commit(bar_ring_empty(slot1));
+                            }
                         }
-                        mma_commit(bar_ring_empty(slot));  // frees the stage when these MMAs have read it
                     }
                     __syncwarp();
-                    a_lo32 += KSTEP_BYTES >> 4;
-                    ta += 16u;
-                    if (++slot == nslots) {
-                        slot = 0;
+                    const int adv = two ? 2 : 1;
+                    a_lo32 += adv * (KSTEP_BYTES >> 4);
+                    ta += 16u * adv;
+                    slot += adv;
+                    if (slot >= nslots) {
+                        slot -= nslots;
                         rphase ^= 1u;
                     }
                 }
@@ -787,7 +831,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 tc_fence_before();
                 if (C.qbuf >= 0) mbar_arrive(bar_q_empty(C.qbuf));
                 const bool last_of_layer = (c == L.first_chunk + L.nchunks - 1);
-                if (out_dst != DST_FINAL && last_of_layer) mbar_arrive(bar_act_ready);
+                if (out_dst != DST_FINAL) mbar_arrive(bar_act_ready(c - L.first_chunk));
                 // the layer-0 operand of the NEXT tile can be written as soon as layer 0 of this tile is done
                 if (half == 0 && C.layer == 0 && last_of_layer) {
                     const long long nt = tile + gridDim.x;

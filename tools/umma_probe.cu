@@ -333,6 +333,78 @@ time_kernel2(int N, int a_tmem, int nmma, long long* out) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512));
 }
 
+
+// Timing v3: G MMAs per elected block (like the real kernel's 3 per stage), descriptors advanced by adds.
+template <int G, int SAME>
+__global__ void __launch_bounds__(128, 1)
+time_kernel3(int N, int a_tmem, int nmma, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < 48 * 1024 / 4; e += 128) reinterpret_cast<uint32_t*>(smem)[e] = 0x3c003c00u + e;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tm = tmem_base_s;
+    if (warp == 0) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t sA = smem_u32(smem), sB = smem_u32(smem) + 16384;
+        const uint64_t da = make_desc(sA, 2048, 128);
+        const uint64_t db = make_desc(sB, (uint32_t)N * 16, 128);
+        const long long t0 = clock64();
+        for (int i = 0; i < nmma; i += G) {
+            if (elect_one()) {
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    const uint64_t dbi = SAME ? db : db + (uint64_t)(u * 64);
+                    const uint64_t dai = SAME ? da : da + (uint64_t)(u * 16);
+                    if (a_tmem)
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tm),
+                                     "r"(tm + 480u), "l"(dbi), "r"(idesc), "r"(1u) : "memory");
+                    else
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tm),
+                                     "l"(dai), "l"(dbi), "r"(idesc), "r"(1u) : "memory");
+                }
+            }
+            __syncwarp();
+        }
+        if (elect_one())
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar)) : "memory");
+        __syncwarp();
+        mbar_wait(&bar, 0, nullptr, 0);
+        const long long t1 = clock64();
+        if ((tid & 31) == 0) out[0] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512));
+}
+template <int G, int SAME>
+static int run3(int N, int a_tmem, long long* d) {
+    const int nmma = 1536;
+    cudaFuncSetAttribute(time_kernel3<G, SAME>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    for (int rep = 0; rep < 2; ++rep) {
+        time_kernel3<G, SAME><<<1, 128, 96 * 1024>>>(N, a_tmem, nmma, d);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+    }
+    long long c = 0;
+    CK(cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost));
+    printf("timing3 N=%d a_tmem=%d G=%d same=%d : %.1f cycles/MMA (floor N/2 = %d)\n", N, a_tmem, G, SAME, (double)c / nmma, N / 2);
+    return 0;
+}
+
 static int run_timing(int argc, char** argv) {
     const int N = argc > 2 ? atoi(argv[2]) : 176;
     const int a_tmem = argc > 3 ? atoi(argv[3]) : 0;
@@ -345,6 +417,13 @@ static int run_timing(int argc, char** argv) {
     cudaFuncSetAttribute(time_kernel2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(time_kernel2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(time_kernel2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (argv[1][1] == '3') {
+        for (int N : {64, 144, 240})
+            for (int at = 0; at < 2; ++at) {
+                run3<1, 0>(N, at, d); run3<3, 0>(N, at, d); run3<6, 0>(N, at, d); run3<12, 0>(N, at, d); run3<6, 1>(N, at, d);
+            }
+        return 0;
+    }
     if (argv[1][1] == '2') {
         const int unroll = argc > 4 ? atoi(argv[4]) : 1;
         for (int rep = 0; rep < 2; ++rep) {
