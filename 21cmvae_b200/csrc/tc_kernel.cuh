@@ -384,6 +384,23 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t ta, uint64_t db, uin
         "r"(ta), "l"(db), "r"(idesc), "r"(acc)
         : "memory");
 }
+// Same with the descriptors passed as 32-bit halves (the high word -- SBO, version -- is constant).
+__device__ __forceinline__ void mma_ss2(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma_ts2(uint32_t d, uint32_t ta, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(d),
+        "r"(ta), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
 }
@@ -507,6 +524,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     const uint32_t tm = *tmem_slot;
     const int n_chunks = P.n_chunks, nslots = P.nslots;
     const uint32_t ring0 = base + P.off_ring, slot_bytes = static_cast<uint32_t>(P.slot_bytes);
+    const uint32_t slot16 = slot_bytes >> 4;
 
     if (warp == 0) {
         // ===================== producer: stream the weight image through the ring ============
@@ -578,8 +596,9 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 const uint32_t idesc = idesc_base | (static_cast<uint32_t>(C.ncols >> 3) << 17);
                 const uint32_t d = tm + static_cast<uint32_t>(C.dcol);
                 const uint32_t b_kg = static_cast<uint32_t>(C.ncols) * 16u;   // bytes between B k-groups
-                const uint32_t b_lbo = (b_kg >> 4) << 16;
                 const uint32_t b_lo16 = (b_kg * 2u) >> 4;                     // hi tile -> lo tile, in 16 B units
+                // low descriptor words: (address >> 4) | (LBO >> 4) << 16; slots are slot16 apart
+                const uint32_t b_base32 = ((ring0 & 0x3FFFFu) >> 4) | ((b_kg >> 4) << 16);
                 const bool ts = (L.a_src == A_TMEM);
                 uint32_t a_lo32 = (((base + (L.a_src == A_SMEM_A0 ? P.off_a0 : P.off_act)) & 0x3FFFFu) >> 4) | a_lbo;
                 uint32_t ta = tm;
@@ -588,11 +607,13 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 for (int s = 0; s < nst; s += 2) {
                     const bool two = (s + 1 < nst);
                     // k-steps s (and s+1) may cross into the next chunk of the producing layer
-                    while (s + (two ? 1 : 0) >= next_src_k) {
-                        const int j = src - P.L[C.layer - 1].first_chunk;
-                        mbar_wait(bar_act_ready(j), (act_cnt[j]++) & 1u);
-                        ++src;
-                        next_src_k = (src < src_end) ? (P.C[src].n0 >> 4) : 0x7fffffff;
+                    if (s + 1 >= next_src_k) {
+                        do {
+                            const int j = src - P.L[C.layer - 1].first_chunk;
+                            mbar_wait(bar_act_ready(j), (act_cnt[j]++) & 1u);
+                            ++src;
+                            next_src_k = (src < src_end) ? (P.C[src].n0 >> 4) : 0x7fffffff;
+                        } while (s + 1 >= next_src_k);
                         tc_fence_after();
                     }
                     // probe both stages' barriers back to back (their ~90-cycle latencies overlap)
@@ -602,52 +623,46 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                         slot1 = 0;
                         ph1 ^= 1u;
                     }
-                    const uint32_t ok0 = mbar_try(bar_ring_full(slot), rphase);
-                    const uint32_t ok1 = two ? mbar_try(bar_ring_full(slot1), ph1) : 1u;
-                    if (!ok0) mbar_wait(bar_ring_full(slot), rphase);
-                    if (!ok1) mbar_wait(bar_ring_full(slot1), ph1);
+                    const uint32_t full0 = bar0 + 8u * slot, full1 = bar0 + 8u * slot1;
+                    uint32_t ok = mbar_try(full0, rphase);
+                    if (two) ok &= mbar_try(full1, ph1);
+                    if (!ok) {
+                        mbar_wait(full0, rphase);
+                        if (two) mbar_wait(full1, ph1);
+                    }
                     tc_fence_after();
-                    const uint32_t b0_lo32 = (((ring0 + slot * slot_bytes) & 0x3FFFFu) >> 4) | b_lbo;
-                    const uint32_t b1_lo32 = (((ring0 + slot1 * slot_bytes) & 0x3FFFFu) >> 4) | b_lbo;
-                    const uint64_t db0_hi = (static_cast<uint64_t>(desc_hi) << 32) | b0_lo32;
-                    const uint64_t db0_lo = db0_hi + b_lo16;
-                    const uint64_t db1_hi = (static_cast<uint64_t>(desc_hi) << 32) | b1_lo32;
-                    const uint64_t db1_lo = db1_hi + b_lo16;
+                    const uint32_t b0 = b_base32 + slot * slot16, b1 = b_base32 + slot1 * slot16;
                     const uint32_t acc0 = s > 0 ? 1u : 0u;
                     if (elect_one()) {
                         if (ts) {
-                            mma_ts(d, ta, db0_hi, idesc, acc0);
-                            mma_ts(d, ta, db0_lo, idesc, 1u);
-                            mma_ts(d, ta + 8u, db0_hi, idesc, 1u);
-                            mma_commit(bar_ring_empty(slot));  // frees the stage when these MMAs have read it
+                            mma_ts2(d, ta, b0, desc_hi, idesc, acc0);
+                            mma_ts2(d, ta, b0 + b_lo16, desc_hi, idesc, 1u);
+                            mma_ts2(d, ta + 8u, b0, desc_hi, idesc, 1u);
+                            mma_commit(full0 + 8u * MAX_SLOTS);  // ring_empty(slot): frees the stage when read
                             if (two) {
-                                mma_ts(d, ta + 16u, db1_hi, idesc, 1u);
-                                mma_ts(d, ta + 16u, db1_lo, idesc, 1u);
-                                mma_ts(d, ta + 24u, db1_hi, idesc, 1u);
-                                mma_commit(bar_ring_empty(slot1));
+                                mma_ts2(d, ta + 16u, b1, desc_hi, idesc, 1u);
+                                mma_ts2(d, ta + 16u, b1 + b_lo16, desc_hi, idesc, 1u);
+                                mma_ts2(d, ta + 24u, b1, desc_hi, idesc, 1u);
+                                mma_commit(full1 + 8u * MAX_SLOTS);
                             }
                         } else {
-                            const uint64_t da_hi = (static_cast<uint64_t>(desc_hi) << 32) | a_lo32;
-                            const uint64_t da_lo = da_hi + ((2u * A_KG_BYTES) >> 4);
-                            mma_ss(d, da_hi, db0_hi, idesc, acc0);
-                            mma_ss(d, da_hi, db0_lo, idesc, 1u);
-                            mma_ss(d, da_lo, db0_hi, idesc, 1u);
-                            mma_commit(bar_ring_empty(slot));
+                            const uint32_t a_lo = a_lo32 + ((2u * A_KG_BYTES) >> 4);
+                            mma_ss2(d, a_lo32, b0, desc_hi, idesc, acc0);
+                            mma_ss2(d, a_lo32, b0 + b_lo16, desc_hi, idesc, 1u);
+                            mma_ss2(d, a_lo, b0, desc_hi, idesc, 1u);
+                            mma_commit(full0 + 8u * MAX_SLOTS);
                             if (two) {
-                                const uint64_t da1_hi = da_hi + (KSTEP_BYTES >> 4);
-                                const uint64_t da1_lo = da_lo + (KSTEP_BYTES >> 4);
-                                mma_ss(d, da1_hi, db1_hi, idesc, 1u);
-                                mma_ss(d, da1_hi, db1_lo, idesc, 1u);
-                                mma_ss(d, da1_lo, db1_hi, idesc, 1u);
-                                mma_commit(bar_ring_empty(slot1));
+                                mma_ss2(d, a_lo32 + (KSTEP_BYTES >> 4), b1, desc_hi, idesc, 1u);
+                                mma_ss2(d, a_lo32 + (KSTEP_BYTES >> 4), b1 + b_lo16, desc_hi, idesc, 1u);
+                                mma_ss2(d, a_lo + (KSTEP_BYTES >> 4), b1, desc_hi, idesc, 1u);
+                                mma_commit(full1 + 8u * MAX_SLOTS);
                             }
                         }
                     }
                     __syncwarp();
-                    const int adv = two ? 2 : 1;
-                    a_lo32 += adv * (KSTEP_BYTES >> 4);
-                    ta += 16u * adv;
-                    slot += adv;
+                    a_lo32 += 2 * (KSTEP_BYTES >> 4);
+                    ta += 32u;
+                    slot += two ? 2 : 1;
                     if (slot >= nslots) {
                         slot -= nslots;
                         rphase ^= 1u;
