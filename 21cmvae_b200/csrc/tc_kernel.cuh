@@ -74,8 +74,12 @@ struct Plan {
     int n_layers, n_chunks;
     int K0;      // true number of input parameters
     int n_out;   // true output width
-    int slot_bytes, nslots;
-    int lookahead;  // MMA warp polls the weight ring two stages ahead
+    int slot_bytes, nslots;      // weight ring, one CTA per tile (cta_group::1)
+    int slot_bytes2, nslots2;    // weight ring of the CTA-pair kernel (cta_group::2: each CTA holds half of every B tile)
+    int smem_total2;
+    int default_cg;              // kernel variant used unless VAE21_TC_CTA_GROUP overrides it
+    int lookahead;  // (unused experiment flag)
+    int dbg;        // ablation bits for profiling (VAE21_TC_DEBUG): 1 no MMA issue, 2 no epilogue work, 4 no weight copies
     int bias_total;
     // shared-memory carve-up (bytes from the 1024-aligned base)
     int off_act, off_stage, off_a0, off_ring, off_bias, off_s0, off_obs, off_isig, off_bar, smem_total;
@@ -121,6 +125,8 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
     if (dims[0] > 16) { why = "more than 16 input parameters"; return false; }
     P.n_layers = n_layers;
     P.lookahead = std::getenv("VAE21_TC_LOOKAHEAD") ? 1 : 0;  // measured slower (2.87 vs 2.72 ms): off by default
+    P.default_cg = 1;
+    P.dbg = std::getenv("VAE21_TC_DEBUG") ? std::atoi(std::getenv("VAE21_TC_DEBUG")) : 0;
     P.K0 = dims[0];
     P.n_out = dims[n_layers];
     auto pad16 = [](int x) { return (x + 15) / 16 * 16; };
@@ -263,16 +269,24 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
     const int avail = SMEM_LIMIT - 128 /*alignment slack*/ - off;
     P.nslots = std::min(MAX_SLOTS, avail / P.slot_bytes);
     if (P.nslots < 2) { why = "shared memory: activations leave no room for a weight ring"; return false; }
+    P.slot_bytes2 = P.slot_bytes / 2;
+    P.nslots2 = std::min(MAX_SLOTS, avail / P.slot_bytes2) & ~1;  // even: the MMA loop consumes slots in pairs
+    P.smem_total2 = off + P.nslots2 * P.slot_bytes2 + 128;
     off += P.nslots * P.slot_bytes;
     P.smem_total = off + 128;
 
-    // weight image, in exactly the order the MMA warp consumes it: chunk -> k-step -> {hi, lo} tile
-    // tile = [2 k-groups][ncols rows][8 elements]  (B operand, "K-major": row n holds W[k][n])
-    for (int f = 0; f < 2; ++f) img[f].assign(P.w_bytes / 2, 0);
+    // Weight images, in exactly the order the MMA warp consumes them: chunk -> k-step -> {hi, lo} tile,
+    // tile = [2 k-groups][rows][8 elements]  (B operand, "K-major": row n holds W[k][n]).
+    // Image 1 (bytes [0, w_bytes)): whole tiles for the one-CTA kernel.
+    // Image 2 (bytes [w_bytes, 2 w_bytes)): for the CTA-pair kernel, rank r's half (rows [r n/2, (r+1) n/2) of
+    // every tile) at w_bytes + r * w_bytes / 2, same order.
+    for (int f = 0; f < 2; ++f) img[f].assign(P.w_bytes, 0);
+    const size_t img2 = P.w_bytes / 2;  // element offset of image 2
     for (int c = 0; c < nchunks; ++c) {
         const Chunk& C = P.C[c];
         const int l = C.layer;
         const int Kt = dims[l], Nt = dims[l + 1];
+        const int hn = C.ncols / 2;
         for (int s = 0; s < C.nstages; ++s) {
             const size_t base = (C.w_off + static_cast<size_t>(s) * C.ncols * 64) / 2;  // in elements
             const size_t lo_base = base + static_cast<size_t>(C.ncols) * 16;
@@ -282,12 +296,21 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
                     const int n = C.n0 + nn;
                     const float w = (k < Kt && n < Nt) ? kernels[l][static_cast<size_t>(k) * Nt + n] : 0.f;
                     const size_t e = (static_cast<size_t>(kk >> 3) * C.ncols + nn) * 8 + (kk & 7);
-                    const unsigned short hb = f2bf16(w);
+                    const int r = nn / hn, nl = nn - r * hn;
+                    const size_t base2 = img2 + static_cast<size_t>(r) * (P.w_bytes / 4) + C.w_off / 4 +
+                                         static_cast<size_t>(s) * C.ncols * 16;
+                    const size_t lo2 = base2 + static_cast<size_t>(hn) * 16;
+                    const size_t e2 = (static_cast<size_t>(kk >> 3) * hn + nl) * 8 + (kk & 7);
+                    const unsigned short hb = f2bf16(w), lb = f2bf16(w - bf162f(hb));
                     img[0][base + e] = hb;
-                    img[0][lo_base + e] = f2bf16(w - bf162f(hb));
-                    const unsigned short hh = f2h16(w);
+                    img[0][lo_base + e] = lb;
+                    img[0][base2 + e2] = hb;
+                    img[0][lo2 + e2] = lb;
+                    const unsigned short hh = f2h16(w), lh = f2h16(w - h162f(hh));
                     img[1][base + e] = hh;
-                    img[1][lo_base + e] = f2h16(w - h162f(hh));
+                    img[1][lo_base + e] = lh;
+                    img[1][base2 + e2] = hh;
+                    img[1][lo2 + e2] = lh;
                 }
             }
         }
@@ -405,6 +428,72 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
 }
 
+
+// ---- CTA-pair (cluster of 2, cta_group::2) helpers ------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(bar),
+        "r"(rank)
+        : "memory");
+}
+// (Default semantics like CUTLASS' ClusterBarrier: a cluster-scope acquire on every probe costs ~400 cycles.)
+__device__ __forceinline__ uint32_t mbar_try_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    long long t0 = 0;
+    unsigned spins = 0;
+    while (!mbar_try_cluster(bar, parity)) {
+        if ((++spins & 1023u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000ll) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void mma2_ss2(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma2_ts2(uint32_t d, uint32_t ta, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(d),
+        "r"(ta), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void mma2_commit_both(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}\n" ::"r"(bar)
+        : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
@@ -449,7 +538,11 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 // ---------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------
-template <int FMT>  // 0: bf16 split, 1: fp16 split
+// CG = 1: one CTA per 128-row tile (cta_group::1).  CG = 2: a cluster of two CTAs works on a 256-row
+// super-tile with cta_group::2 MMAs (M = 256): rank 0 issues every MMA for both CTAs, each CTA streams
+// HALF of every weight tile into its own shared memory and runs its own epilogue on its own 128 rows.
+// The MMA-issuing warp -- the limiter of the one-CTA kernel -- then serves twice the rows per instruction.
+template <int FMT, int CG>  // FMT 0: bf16 split, 1: fp16 split
 __global__ void __launch_bounds__(NTHREADS, 1)
 vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormConsts nc, const __grid_constant__ LaunchArgs a,
                 const uint8_t* __restrict__ wimg, const float* __restrict__ bias_g) {
@@ -459,7 +552,13 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     uint8_t* sm = smem_raw + (base - raw);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long ntiles = (a.n + MT - 1) / MT;
+    constexpr bool PAIR = (CG == 2);
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = (rank == 0);
+    // work units: 128-row tiles (CG 1) or 256-row super-tiles (CG 2); this CTA's tile of unit u is CG*u + rank
+    const long long nunits = (a.n + CG * MT - 1) / (CG * MT);
+    const long long unit0 = blockIdx.x / CG, ustep = gridDim.x / CG;
+    const long long ntiles = nunits;  // (loop bound below)
 
     // barrier addresses
     const uint32_t bar0 = base + P.off_bar;
@@ -481,14 +580,16 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
 
     // ---- one-time setup -------------------------------------------------------------------
     if (tid == 0) {
-        for (int s = 0; s < P.nslots; ++s) {
-            mbar_init(bar_ring_full(s), 1);
+        for (int s = 0; s < (PAIR ? P.nslots2 : P.nslots); ++s) {
+            // pair leader: its own producer (arrive + tx bytes) and the peer's forwarded "my half landed"
+            mbar_init(bar_ring_full(s), (PAIR && leader) ? 2 : 1);
             mbar_init(bar_ring_empty(s), 1);
         }
+        const uint32_t fwd = (PAIR && leader) ? 1u : 0u;  // + one forwarded arrival from the peer CTA
         for (int i = 0; i < NFULL; ++i) mbar_init(bar_chunk_full(i), 1);
-        for (int b = 0; b < 2; ++b) mbar_init(bar_q_empty(b), NEPI);
-        for (int j = 0; j < MAX_LCHUNK; ++j) mbar_init(bar_act_ready(j), NEPI);
-        mbar_init(bar_a0_ready, 128);
+        for (int b = 0; b < 2; ++b) mbar_init(bar_q_empty(b), NEPI + fwd);
+        for (int j = 0; j < MAX_LCHUNK; ++j) mbar_init(bar_act_ready(j), NEPI + fwd);
+        mbar_init(bar_a0_ready, 128 + fwd);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (tid < 16) {
@@ -515,15 +616,21 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         }
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // both CTAs: barriers initialised and TMEM allocated before any cross-CTA traffic
     tc_fence_after();
     const uint32_t tm = *tmem_slot;
-    const int n_chunks = P.n_chunks, nslots = P.nslots;
-    const uint32_t ring0 = base + P.off_ring, slot_bytes = static_cast<uint32_t>(P.slot_bytes);
+    const int n_chunks = P.n_chunks, nslots = PAIR ? P.nslots2 : P.nslots;
+    const uint32_t ring0 = base + P.off_ring, slot_bytes = static_cast<uint32_t>(PAIR ? P.slot_bytes2 : P.slot_bytes);
     const uint32_t slot16 = slot_bytes >> 4;
 
     if (warp == 0) {
@@ -531,20 +638,25 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         if (lane == 0) {
             int slot = 0;
             uint32_t phase = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (long long unit = unit0; unit < nunits; unit += ustep) {
                 for (int c = 0; c < n_chunks; ++c) {
                     const Chunk& C = P.C[c];
-                    const uint32_t bytes = static_cast<uint32_t>(C.ncols) * 64u;
-                    const uint8_t* src = wimg + C.w_off;
+                    const uint32_t bytes = static_cast<uint32_t>(C.ncols) * (PAIR ? 32u : 64u);
+                    const uint8_t* src = PAIR ? wimg + P.w_bytes + static_cast<size_t>(rank) * (P.w_bytes / 2) + C.w_off / 2
+                                              : wimg + C.w_off;
                     const int nst = C.nstages;
                     for (int s = 0; s < nst; ++s) {
                         mbar_wait(bar_ring_empty(slot), phase ^ 1u);
+                        if (P.dbg & 4) {
+                            mbar_arrive(bar_ring_full(slot));
+                        } else {
                         mbar_expect_tx(bar_ring_full(slot), bytes);
                         asm volatile(
                             "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
                                 ring0 + slot * slot_bytes),
                             "l"(src), "r"(bytes), "r"(bar_ring_full(slot))
                             : "memory");
+                        }
                         src += bytes;
                         if (++slot == nslots) {
                             slot = 0;
@@ -566,11 +678,25 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         uint32_t act_cnt[MAX_LCHUNK] = {0, 0, 0, 0};
         uint32_t a0_cnt = 0;
         const uint32_t fmtbits = (FMT == 0) ? 1u : 0u;
-        const uint32_t idesc_base = (1u << 4) | (fmtbits << 7) | (fmtbits << 10) | ((128u >> 4) << 24);
+        const uint32_t idesc_base = (1u << 4) | (fmtbits << 7) | (fmtbits << 10) | ((static_cast<uint32_t>(CG * 128) >> 4) << 24);
         // descriptor high words are constant: SBO = 128 B, version 1; LBO goes into the low word
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);
         const uint32_t a_lbo = (static_cast<uint32_t>(A_KG_BYTES) >> 4) << 16;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // In the CTA-pair kernel rank 0 issues; rank 1 runs the SAME schedule as a forwarder: wherever the
+        // issuer waits for an event, the forwarder waits for its own CTA's instance of it and then arrives on
+        // the issuer's barrier (which counts the local arrivals plus this one).
+        auto sync_event = [&](uint32_t bar, uint32_t parity) {
+            if (!PAIR) {
+                mbar_wait(bar, parity);
+            } else if (leader) {
+                mbar_wait_cluster(bar, parity);
+            } else {
+                mbar_wait(bar, parity);
+                if (lane == 0) mbar_arrive_remote(bar, 0);
+                __syncwarp();
+            }
+        };
+        for (long long unit = unit0; unit < nunits; unit += ustep) {
             for (int c = 0; c < n_chunks; ++c) {
                 const Chunk& C = P.C[c];
                 const Layer& L = P.L[C.layer];
@@ -580,7 +706,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 int src = -1, src_end = -1;  // chunks of the producing layer still to wait for
                 if (c == L.first_chunk) {
                     if (C.layer == 0) {
-                        mbar_wait(bar_a0_ready, a0_cnt & 1u);
+                        sync_event(bar_a0_ready, a0_cnt & 1u);
                         ++a0_cnt;
                     } else {
                         src = P.L[C.layer - 1].first_chunk;
@@ -590,13 +716,13 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 if (C.qbuf >= 0) {  // accumulator buffer must have been drained by the epilogue
                     const uint32_t u = C.qbuf ? q_use1 : q_use0;
                     if (C.qbuf) ++q_use1; else ++q_use0;
-                    if (u > 0) mbar_wait(bar_q_empty(C.qbuf), (u - 1u) & 1u);
+                    if (u > 0) sync_event(bar_q_empty(C.qbuf), (u - 1u) & 1u);
                 }
                 tc_fence_after();
                 const uint32_t idesc = idesc_base | (static_cast<uint32_t>(C.ncols >> 3) << 17);
                 const uint32_t d = tm + static_cast<uint32_t>(C.dcol);
-                const uint32_t b_kg = static_cast<uint32_t>(C.ncols) * 16u;   // bytes between B k-groups
-                const uint32_t b_lo16 = (b_kg * 2u) >> 4;                     // hi tile -> lo tile, in 16 B units
+                const uint32_t b_kg = static_cast<uint32_t>(C.ncols / CG) * 16u;  // bytes between B k-groups (this CTA's rows)
+                const uint32_t b_lo16 = (b_kg * 2u) >> 4;                         // hi tile -> lo tile, in 16 B units
                 // low descriptor words: (address >> 4) | (LBO >> 4) << 16; slots are slot16 apart
                 const uint32_t b_base32 = ((ring0 & 0x3FFFFu) >> 4) | ((b_kg >> 4) << 16);
                 const bool ts = (L.a_src == A_TMEM);
@@ -610,13 +736,12 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                     if (s + 1 >= next_src_k) {
                         do {
                             const int j = src - P.L[C.layer - 1].first_chunk;
-                            mbar_wait(bar_act_ready(j), (act_cnt[j]++) & 1u);
+                            sync_event(bar_act_ready(j), (act_cnt[j]++) & 1u);
                             ++src;
                             next_src_k = (src < src_end) ? (P.C[src].n0 >> 4) : 0x7fffffff;
                         } while (s + 1 >= next_src_k);
                         tc_fence_after();
                     }
-                    // probe both stages' barriers back to back (their ~90-cycle latencies overlap)
                     int slot1 = slot + 1;
                     uint32_t ph1 = rphase;
                     if (slot1 == nslots) {
@@ -624,42 +749,92 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                         ph1 ^= 1u;
                     }
                     const uint32_t full0 = bar0 + 8u * slot, full1 = bar0 + 8u * slot1;
-                    uint32_t ok = mbar_try(full0, rphase);
-                    if (two) ok &= mbar_try(full1, ph1);
-                    if (!ok) {
+                    if (PAIR && !leader) {
+                        // forwarder: my halves of these stages have landed -> tell the issuer
                         mbar_wait(full0, rphase);
-                        if (two) mbar_wait(full1, ph1);
-                    }
-                    tc_fence_after();
-                    const uint32_t b0 = b_base32 + slot * slot16, b1 = b_base32 + slot1 * slot16;
-                    const uint32_t acc0 = s > 0 ? 1u : 0u;
-                    if (elect_one()) {
-                        if (ts) {
-                            mma_ts2(d, ta, b0, desc_hi, idesc, acc0);
-                            mma_ts2(d, ta, b0 + b_lo16, desc_hi, idesc, 1u);
-                            mma_ts2(d, ta + 8u, b0, desc_hi, idesc, 1u);
-                            mma_commit(full0 + 8u * MAX_SLOTS);  // ring_empty(slot): frees the stage when read
-                            if (two) {
-                                mma_ts2(d, ta + 16u, b1, desc_hi, idesc, 1u);
-                                mma_ts2(d, ta + 16u, b1 + b_lo16, desc_hi, idesc, 1u);
-                                mma_ts2(d, ta + 24u, b1, desc_hi, idesc, 1u);
-                                mma_commit(full1 + 8u * MAX_SLOTS);
-                            }
-                        } else {
-                            const uint32_t a_lo = a_lo32 + ((2u * A_KG_BYTES) >> 4);
-                            mma_ss2(d, a_lo32, b0, desc_hi, idesc, acc0);
-                            mma_ss2(d, a_lo32, b0 + b_lo16, desc_hi, idesc, 1u);
-                            mma_ss2(d, a_lo, b0, desc_hi, idesc, 1u);
-                            mma_commit(full0 + 8u * MAX_SLOTS);
-                            if (two) {
-                                mma_ss2(d, a_lo32 + (KSTEP_BYTES >> 4), b1, desc_hi, idesc, 1u);
-                                mma_ss2(d, a_lo32 + (KSTEP_BYTES >> 4), b1 + b_lo16, desc_hi, idesc, 1u);
-                                mma_ss2(d, a_lo + (KSTEP_BYTES >> 4), b1, desc_hi, idesc, 1u);
-                                mma_commit(full1 + 8u * MAX_SLOTS);
+                        if (lane == 0) mbar_arrive_remote(full0, 0);
+                        if (two) {
+                            mbar_wait(full1, ph1);
+                            if (lane == 0) mbar_arrive_remote(full1, 0);
+                        }
+                        __syncwarp();
+                    } else {
+                        // probe both stages' barriers back to back (their ~90-cycle latencies overlap)
+                        uint32_t ok = PAIR ? mbar_try_cluster(full0, rphase) : mbar_try(full0, rphase);
+                        if (two) ok &= PAIR ? mbar_try_cluster(full1, ph1) : mbar_try(full1, ph1);
+                        if (!ok) {
+                            if (PAIR) {
+                                mbar_wait_cluster(full0, rphase);
+                                if (two) mbar_wait_cluster(full1, ph1);
+                            } else {
+                                mbar_wait(full0, rphase);
+                                if (two) mbar_wait(full1, ph1);
                             }
                         }
+                        tc_fence_after();
+                        const uint32_t b0 = b_base32 + slot * slot16, b1 = b_base32 + slot1 * slot16;
+                        const uint32_t acc0 = s > 0 ? 1u : 0u;
+                        const uint32_t a_lo = a_lo32 + ((2u * A_KG_BYTES) >> 4);
+                        const uint32_t a1 = a_lo32 + (KSTEP_BYTES >> 4), a1_lo = a_lo + (KSTEP_BYTES >> 4);
+                        if (elect_one()) {
+                            if (P.dbg & 1) {
+                                if (PAIR) {
+                                    mma2_commit_both(full0 + 8u * MAX_SLOTS);
+                                    if (two) mma2_commit_both(full1 + 8u * MAX_SLOTS);
+                                } else {
+                                    mma_commit(full0 + 8u * MAX_SLOTS);
+                                    if (two) mma_commit(full1 + 8u * MAX_SLOTS);
+                                }
+                            } else if (PAIR) {
+                                if (ts) {
+                                    mma2_ts2(d, ta, b0, desc_hi, idesc, acc0);
+                                    mma2_ts2(d, ta, b0 + b_lo16, desc_hi, idesc, 1u);
+                                    mma2_ts2(d, ta + 8u, b0, desc_hi, idesc, 1u);
+                                } else {
+                                    mma2_ss2(d, a_lo32, b0, desc_hi, idesc, acc0);
+                                    mma2_ss2(d, a_lo32, b0 + b_lo16, desc_hi, idesc, 1u);
+                                    mma2_ss2(d, a_lo, b0, desc_hi, idesc, 1u);
+                                }
+                                mma2_commit_both(full0 + 8u * MAX_SLOTS);  // ring_empty(slot) in both CTAs
+                                if (two) {
+                                    if (ts) {
+                                        mma2_ts2(d, ta + 16u, b1, desc_hi, idesc, 1u);
+                                        mma2_ts2(d, ta + 16u, b1 + b_lo16, desc_hi, idesc, 1u);
+                                        mma2_ts2(d, ta + 24u, b1, desc_hi, idesc, 1u);
+                                    } else {
+                                        mma2_ss2(d, a1, b1, desc_hi, idesc, 1u);
+                                        mma2_ss2(d, a1, b1 + b_lo16, desc_hi, idesc, 1u);
+                                        mma2_ss2(d, a1_lo, b1, desc_hi, idesc, 1u);
+                                    }
+                                    mma2_commit_both(full1 + 8u * MAX_SLOTS);
+                                }
+                            } else {
+                                if (ts) {
+                                    mma_ts2(d, ta, b0, desc_hi, idesc, acc0);
+                                    mma_ts2(d, ta, b0 + b_lo16, desc_hi, idesc, 1u);
+                                    mma_ts2(d, ta + 8u, b0, desc_hi, idesc, 1u);
+                                } else {
+                                    mma_ss2(d, a_lo32, b0, desc_hi, idesc, acc0);
+                                    mma_ss2(d, a_lo32, b0 + b_lo16, desc_hi, idesc, 1u);
+                                    mma_ss2(d, a_lo, b0, desc_hi, idesc, 1u);
+                                }
+                                mma_commit(full0 + 8u * MAX_SLOTS);  // ring_empty(slot): frees the stage when read
+                                if (two) {
+                                    if (ts) {
+                                        mma_ts2(d, ta + 16u, b1, desc_hi, idesc, 1u);
+                                        mma_ts2(d, ta + 16u, b1 + b_lo16, desc_hi, idesc, 1u);
+                                        mma_ts2(d, ta + 24u, b1, desc_hi, idesc, 1u);
+                                    } else {
+                                        mma_ss2(d, a1, b1, desc_hi, idesc, 1u);
+                                        mma_ss2(d, a1, b1 + b_lo16, desc_hi, idesc, 1u);
+                                        mma_ss2(d, a1_lo, b1, desc_hi, idesc, 1u);
+                                    }
+                                    mma_commit(full1 + 8u * MAX_SLOTS);
+                                }
+                            }
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                     a_lo32 += 2 * (KSTEP_BYTES >> 4);
                     ta += 32u;
                     slot += two ? 2 : 1;
@@ -668,8 +843,13 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                         rphase ^= 1u;
                     }
                 }
-                if (elect_one()) mma_commit(bar_chunk_full(seq & (NFULL - 1)));
-                __syncwarp();
+                if (!PAIR || leader) {
+                    if (elect_one()) {
+                        if (PAIR) mma2_commit_both(bar_chunk_full(seq & (NFULL - 1)));
+                        else mma_commit(bar_chunk_full(seq & (NFULL - 1)));
+                    }
+                    __syncwarp();
+                }
                 ++seq;
             }
         }
@@ -732,9 +912,10 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             mbar_arrive(bar_a0_ready);
         };
 
-        if (half == 0 && static_cast<long long>(blockIdx.x) < ntiles) write_a0(blockIdx.x);
+        if (half == 0 && unit0 < nunits) write_a0(CG * unit0 + rank);
 
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        for (long long unit = unit0; unit < nunits; unit += ustep, ++tcount) {
+            const long long tile = CG * unit + rank;
             const long long grow = tile * MT + row;
             const bool full_tile = (tile * MT + MT <= a.n);
             // output pointer of (row 32*sub + lane/16, column lane%16): each store instruction of the final layer
@@ -826,7 +1007,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 };
                 // software-pipelined accumulator reads: the load of this warp's next group is in flight while
                 // the current one is converted
-                if (half < ng) {
+                if (half < ng && !(P.dbg & 2)) {
                     uint32_t ra[16], rb[16];
                     tmem_ld16(tbase + static_cast<uint32_t>(16 * half), ra);
                     for (int g = half; g < ng; g += 4) {
@@ -849,8 +1030,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 if (out_dst != DST_FINAL) mbar_arrive(bar_act_ready(c - L.first_chunk));
                 // the layer-0 operand of the NEXT tile can be written as soon as layer 0 of this tile is done
                 if (half == 0 && C.layer == 0 && last_of_layer) {
-                    const long long nt = tile + gridDim.x;
-                    if (nt < ntiles) write_a0(nt);
+                    if (unit + ustep < nunits) write_a0(CG * (unit + ustep) + rank);
                 }
             }
             // tile end: all epilogue warps meet (the output staging tiles alias the activation buffer, and the
@@ -880,28 +1060,55 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     // ---- teardown -------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // no CTA frees TMEM / exits while its peer may still signal it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512));
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512));
     }
 }
 
-inline cudaError_t prepare() {
-    cudaError_t e = cudaFuncSetAttribute(vae21_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(vae21_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+template <int FMT, int CG>
+inline cudaError_t launch_one(const Plan& P, const NormConsts& nc, const LaunchArgs& a, const uint8_t* wimg, const float* bias,
+                              int grid, cudaStream_t st) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = CG == 2 ? P.smem_total2 : P.smem_total;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, vae21_tc_kernel<FMT, CG>, P, nc, a, wimg, bias);
 }
 
+inline cudaError_t prepare() {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(vae21_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(vae21_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(vae21_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(vae21_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+}
+
+// cta_group: 1 = one CTA per 128-row tile, 2 = CTA pairs on 256-row super-tiles
 inline cudaError_t launch(const Plan& P, const NormConsts& nc, const LaunchArgs& a, const void* wimg, const float* bias,
                           int fmt, int sm_count, cudaStream_t st) {
+    if (a.n <= 0) return cudaSuccess;
+    static const int cg_env = std::getenv("VAE21_TC_CTA_GROUP") ? std::atoi(std::getenv("VAE21_TC_CTA_GROUP")) : 0;
+    const int cg = (cg_env == 1 || cg_env == 2) ? cg_env : P.default_cg;
+    const uint8_t* w = static_cast<const uint8_t*>(wimg);
+    if (cg == 2) {
+        const long long nunits = (a.n + 2 * MT - 1) / (2 * MT);
+        const int grid = 2 * static_cast<int>(std::min<long long>(nunits, sm_count / 2));
+        return fmt == 0 ? launch_one<0, 2>(P, nc, a, w, bias, grid, st) : launch_one<1, 2>(P, nc, a, w, bias, grid, st);
+    }
     const long long ntiles = (a.n + MT - 1) / MT;
-    if (ntiles == 0) return cudaSuccess;
     const int grid = static_cast<int>(std::min<long long>(ntiles, sm_count));
-    if (fmt == 0)
-        vae21_tc_kernel<0><<<grid, NTHREADS, P.smem_total, st>>>(P, nc, a, static_cast<const uint8_t*>(wimg), bias);
-    else
-        vae21_tc_kernel<1><<<grid, NTHREADS, P.smem_total, st>>>(P, nc, a, static_cast<const uint8_t*>(wimg), bias);
-    return cudaGetLastError();
+    return fmt == 0 ? launch_one<0, 1>(P, nc, a, w, bias, grid, st) : launch_one<1, 1>(P, nc, a, w, bias, grid, st);
 }
 
 }  // namespace tck

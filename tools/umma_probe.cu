@@ -454,6 +454,108 @@ static int run_timing(int argc, char** argv) {
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Cluster probe: can a 1-D bulk copy issued by CTA 1 into ITS OWN shared memory signal (complete_tx) a
+// barrier that lives in CTA 0?  And what does a remote mbarrier arrive cost?
+//   umma_probe c
+// ---------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64, 1)
+cluster_kernel(const uint32_t* __restrict__ src, uint32_t* out, long long* cyc, int mode) {
+    __shared__ __align__(128) uint32_t buf[1024];
+    __shared__ __align__(8) uint64_t bar;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 1024; i += 64) buf[i] = 0;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+    }
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    if (mode == 0) {
+        // CTA 0 arms its barrier with the byte count; CTA 1 copies into its own buffer, signalling CTA 0's barrier
+        if (rank == 0 && tid == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&bar)), "r"(4096u) : "memory");
+        asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        if (rank == 1 && tid == 0) {
+            uint32_t rbar;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(rbar) : "r"(smem_u32(&bar)), "r"(0u));
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(buf)),
+                         "l"(src), "r"(4096u), "r"(rbar)
+                         : "memory");
+        }
+        if (rank == 0) {
+            if (tid == 0) {
+                int flag = 0;
+                const bool ok = mbar_wait(&bar, 0, &flag, 1);
+                out[2048] = ok ? 1u : 0u;
+            }
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        if (rank == 1) for (int i = tid; i < 1024; i += 64) out[i] = buf[i];
+    } else {
+        // remote arrive cost: CTA 1 arrives N times on CTA 0's barrier (count 1 -> a phase per arrive), CTA 0 waits each
+        const int N = 256;
+        if (rank == 1 && tid == 0) {
+            uint32_t rbar;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(rbar) : "r"(smem_u32(&bar)), "r"(0u));
+            const long long t0 = clock64();
+            for (int i = 0; i < N; ++i) {
+                if (mode == 1) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(rbar) : "memory");
+                else asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(rbar) : "memory");
+                // wait until CTA 0 consumed it (it bumps a flag in my smem) to avoid phase overrun
+                while (atomicAdd(&buf[0], 0) != (uint32_t)(i + 1)) {}
+            }
+            cyc[0] = clock64() - t0;
+        }
+        if (rank == 0 && tid == 0) {
+            uint32_t rflag;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(rflag) : "r"(smem_u32(&buf[0])), "r"(1u));
+            for (int i = 0; i < N; ++i) {
+                mbar_wait(&bar, i & 1, nullptr, 0);
+                asm volatile("st.shared::cluster.u32 [%0], %1;\n" ::"r"(rflag), "r"((uint32_t)(i + 1)) : "memory");
+            }
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    }
+}
+static int run_cluster() {
+    uint32_t *dsrc, *dout;
+    long long* dc;
+    std::vector<uint32_t> h(1024);
+    for (int i = 0; i < 1024; ++i) h[i] = 0xabc00000u + i;
+    CK(cudaMalloc(&dsrc, 4096));
+    CK(cudaMalloc(&dout, 4 * 4096));
+    CK(cudaMalloc(&dc, 8));
+    CK(cudaMemcpy(dsrc, h.data(), 4096, cudaMemcpyHostToDevice));
+    // mode 0 (bulk copy signalling a barrier of the OTHER CTA) faults with 'unspecified launch failure' on B200:
+    // the mbarrier of cp.async.bulk must live in the destination CTA.  Kept for the record, not run by default.
+    for (int mode = (getenv("PROBE_REMOTE_TX") ? 0 : 1); mode < 3; ++mode) {
+        CK(cudaMemset(dout, 0, 4 * 4096));
+        cluster_kernel<<<2, 64>>>(dsrc, dout, dc, mode);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            printf("cluster mode %d: CUDA error %s\n", mode, cudaGetErrorString(e));
+            return 2;
+        }
+        if (mode == 0) {
+            std::vector<uint32_t> o(2049);
+            CK(cudaMemcpy(o.data(), dout, 2049 * 4, cudaMemcpyDeviceToHost));
+            int bad = 0;
+            for (int i = 0; i < 1024; ++i) bad += (o[i] != h[i]);
+            printf("cluster: bulk copy by CTA1 into own smem signalling CTA0's barrier: wait_ok=%u data_mismatch=%d  %s\n", o[2048], bad,
+                   (o[2048] == 1 && bad == 0) ? "PASS" : "FAIL");
+        } else {
+            long long c = 0;
+            CK(cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost));
+            printf("cluster: remote arrive (%s) + consume round trip: %.0f cycles\n", mode == 1 ? "release" : "relaxed", (double)c / 256);
+        }
+    }
+    return 0;
+}
+
 static uint16_t to16(float x, int fp16) {
     if (fp16) {
         __half h = __float2half_rn(x);
@@ -486,6 +588,7 @@ int main(int argc, char** argv) {
         printf("%d\n", nvar);
         return 0;
     }
+    if (argv[1][0] == 'c') return run_cluster();
     if (argv[1][0] == 't') return run_timing(argc, argv);
     const int vi = atoi(argv[1]);
     if (vi < 0 || vi >= nvar) return 1;
