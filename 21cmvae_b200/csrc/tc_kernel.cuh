@@ -36,11 +36,15 @@
 namespace tck {
 
 constexpr int MT = 128;
-constexpr int NTHREADS = 320;   // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int NTHREADS = 352;   // warp 0 producer, warps 1 and 10 MMA issuers, warps 2..9 epilogue
 constexpr int NEPI = 256;       // epilogue threads
 constexpr int MAXL = 8;
 constexpr int MAXC = 32;
 constexpr int NFULL = 4;          // ring of "accumulator chunk ready" barriers
+#ifndef VAE21_TC_ABLATE
+#define VAE21_TC_ABLATE 0  // profiling only: 1 no MMA issue, 2 no epilogue work, 4 no weight copies (bit mask)
+#endif
+constexpr int DBG = VAE21_TC_ABLATE;
 constexpr int MAX_SLOTS = 8;
 constexpr int MAX_LCHUNK = 4;      // chunks per non-final layer (per-chunk operand-ready barriers)
 constexpr int SMEM_LIMIT = 227 * 1024;
@@ -586,8 +590,9 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             mbar_init(bar_ring_empty(s), 1);
         }
         const uint32_t fwd = (PAIR && leader) ? 1u : 0u;  // + one forwarded arrival from the peer CTA
-        for (int i = 0; i < NFULL; ++i) mbar_init(bar_chunk_full(i), 1);
+        for (int i = 0; i < NFULL; ++i) mbar_init(bar_chunk_full(i), 2);
         for (int b = 0; b < 2; ++b) mbar_init(bar_q_empty(b), NEPI + fwd);
+        // (chunk_full: one commit from each of the two issuing warps)
         for (int j = 0; j < MAX_LCHUNK; ++j) mbar_init(bar_act_ready(j), NEPI + fwd);
         mbar_init(bar_a0_ready, 128 + fwd);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -647,7 +652,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                     const int nst = C.nstages;
                     for (int s = 0; s < nst; ++s) {
                         mbar_wait(bar_ring_empty(slot), phase ^ 1u);
-                        if (P.dbg & 4) {
+                        if (DBG & 4) {
                             mbar_arrive(bar_ring_full(slot));
                         } else {
                         mbar_expect_tx(bar_ring_full(slot), bytes);
@@ -666,8 +671,14 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer ====================================================
+    } else if (warp == 1 || warp == 10) {
+        // ===================== MMA issuers ===================================================
+        // Two warps share the issue work (one warp alone is the limiter: ~100 instructions per 6 MMAs at the
+        // latency-bound rate of a lone warp).  Within an accumulator chunk warp mw issues the pair-iterations
+        // with (iteration & 1) == mw.  Ordering between the two issuers is established once per chunk: after
+        // warp 0 has issued iteration 0 (which overwrites the accumulator) both meet at a named barrier bracketed
+        // by tcgen05 fences, so everything warp 1 issues is ordered after it.
+        const int mw = (warp == 1) ? 0 : 1;
         // The whole warp runs this (warp-uniform) loop and only the tcgen05 instructions are
         // predicated on one elected lane: measured with tools/umma_probe.cu, a loop inside an
         // `if (lane == 0)` branch costs 269 cycles per MMA, this form 96..131.
@@ -692,7 +703,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 mbar_wait_cluster(bar, parity);
             } else {
                 mbar_wait(bar, parity);
-                if (lane == 0) mbar_arrive_remote(bar, 0);
+                if (mw == 0 && lane == 0) mbar_arrive_remote(bar, 0);
                 __syncwarp();
             }
         };
@@ -718,6 +729,10 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                     if (C.qbuf) ++q_use1; else ++q_use0;
                     if (u > 0) sync_event(bar_q_empty(C.qbuf), (u - 1u) & 1u);
                 }
+                // chunk-start rendezvous of the two issuers: every MMA of earlier chunks (either warp) is ordered before
+                // the first MMA of this chunk, which may overwrite TMEM columns those MMAs read
+                tc_fence_before();
+                asm volatile("bar.sync 2, 64;\n" ::: "memory");
                 tc_fence_after();
                 const uint32_t idesc = idesc_base | (static_cast<uint32_t>(C.ncols >> 3) << 17);
                 const uint32_t d = tm + static_cast<uint32_t>(C.dcol);
@@ -749,7 +764,10 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                         ph1 ^= 1u;
                     }
                     const uint32_t full0 = bar0 + 8u * slot, full1 = bar0 + 8u * slot1;
-                    if (PAIR && !leader) {
+                    const bool mine = (((s >> 1) & 1) == mw);
+                    if (!mine) {
+                        // the other issuing warp handles this iteration
+                    } else if (PAIR && !leader) {
                         // forwarder: my halves of these stages have landed -> tell the issuer
                         mbar_wait(full0, rphase);
                         if (lane == 0) mbar_arrive_remote(full0, 0);
@@ -777,7 +795,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                         const uint32_t a_lo = a_lo32 + ((2u * A_KG_BYTES) >> 4);
                         const uint32_t a1 = a_lo32 + (KSTEP_BYTES >> 4), a1_lo = a_lo + (KSTEP_BYTES >> 4);
                         if (elect_one()) {
-                            if (P.dbg & 1) {
+                            if (DBG & 1) {
                                 if (PAIR) {
                                     mma2_commit_both(full0 + 8u * MAX_SLOTS);
                                     if (two) mma2_commit_both(full1 + 8u * MAX_SLOTS);
@@ -834,6 +852,12 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                             }
                         }
                         __syncwarp();
+                    }
+                    if (s == 0) {
+                        // rendezvous of the two issuers: iteration 0 (accumulator overwrite) is issued, order the rest after it
+                        tc_fence_before();
+                        asm volatile("bar.sync 2, 64;\n" ::: "memory");
+                        tc_fence_after();
                     }
                     a_lo32 += 2 * (KSTEP_BYTES >> 4);
                     ta += 32u;
@@ -1007,7 +1031,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 };
                 // software-pipelined accumulator reads: the load of this warp's next group is in flight while
                 // the current one is converted
-                if (half < ng && !(P.dbg & 2)) {
+                if (half < ng && !(DBG & 2)) {
                     uint32_t ra[16], rb[16];
                     tmem_ld16(tbase + static_cast<uint32_t>(16 * half), ra);
                     for (int g = half; g < ng; g += 4) {
