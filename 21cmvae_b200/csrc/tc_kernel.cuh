@@ -82,6 +82,7 @@ struct Plan {
     int slot_bytes2, nslots2;    // weight ring of the CTA-pair kernel (cta_group::2: each CTA holds half of every B tile)
     int smem_total2;
     int default_cg;              // kernel variant used unless VAE21_TC_CTA_GROUP overrides it
+    int issuers;                 // MMA-issuing warps: 2 (default) or 1 (VAE21_TC_DETERMINISTIC=1: bitwise reproducible sums)
     int lookahead;  // (unused experiment flag)
     int dbg;        // ablation bits for profiling (VAE21_TC_DEBUG): 1 no MMA issue, 2 no epilogue work, 4 no weight copies
     int bias_total;
@@ -129,7 +130,8 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
     if (dims[0] > 16) { why = "more than 16 input parameters"; return false; }
     P.n_layers = n_layers;
     P.lookahead = std::getenv("VAE21_TC_LOOKAHEAD") ? 1 : 0;  // measured slower (2.87 vs 2.72 ms): off by default
-    P.default_cg = 1;
+    P.default_cg = 2;
+    P.issuers = std::getenv("VAE21_TC_DETERMINISTIC") ? 1 : 2;
     P.dbg = std::getenv("VAE21_TC_DEBUG") ? std::atoi(std::getenv("VAE21_TC_DEBUG")) : 0;
     P.K0 = dims[0];
     P.n_out = dims[n_layers];
@@ -273,7 +275,9 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
     const int avail = SMEM_LIMIT - 128 /*alignment slack*/ - off;
     P.nslots = std::min(MAX_SLOTS, avail / P.slot_bytes);
     if (P.nslots < 2) { why = "shared memory: activations leave no room for a weight ring"; return false; }
-    P.slot_bytes2 = P.slot_bytes / 2;
+    // pair kernel: each CTA holds half of every B tile, so a slot of the same size holds TWO k-steps: the same bytes
+    // in flight with half as many barrier round trips (the ring protocol is latency-, not bandwidth-bound)
+    P.slot_bytes2 = P.slot_bytes;
     P.nslots2 = std::min(MAX_SLOTS, avail / P.slot_bytes2) & ~1;  // even: the MMA loop consumes slots in pairs
     P.smem_total2 = off + P.nslots2 * P.slot_bytes2 + 128;
     off += P.nslots * P.slot_bytes;
@@ -557,6 +561,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr bool PAIR = (CG == 2);
+    constexpr int KPS = PAIR ? 2 : 1;  // k-steps per ring slot
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = (rank == 0);
     // work units: 128-row tiles (CG 1) or 256-row super-tiles (CG 2); this CTA's tile of unit u is CG*u + rank
@@ -590,7 +595,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             mbar_init(bar_ring_empty(s), 1);
         }
         const uint32_t fwd = (PAIR && leader) ? 1u : 0u;  // + one forwarded arrival from the peer CTA
-        for (int i = 0; i < NFULL; ++i) mbar_init(bar_chunk_full(i), 2);
+        for (int i = 0; i < NFULL; ++i) mbar_init(bar_chunk_full(i), P.issuers);
         for (int b = 0; b < 2; ++b) mbar_init(bar_q_empty(b), NEPI + fwd);
         // (chunk_full: one commit from each of the two issuing warps)
         for (int j = 0; j < MAX_LCHUNK; ++j) mbar_init(bar_act_ready(j), NEPI + fwd);
@@ -650,18 +655,20 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                     const uint8_t* src = PAIR ? wimg + P.w_bytes + static_cast<size_t>(rank) * (P.w_bytes / 2) + C.w_off / 2
                                               : wimg + C.w_off;
                     const int nst = C.nstages;
-                    for (int s = 0; s < nst; ++s) {
+                    for (int s = 0; s < nst; s += KPS) {
+                        const uint32_t sbytes = bytes * static_cast<uint32_t>(min(KPS, nst - s));  // k-steps in this slot
                         mbar_wait(bar_ring_empty(slot), phase ^ 1u);
                         if (DBG & 4) {
                             mbar_arrive(bar_ring_full(slot));
                         } else {
-                        mbar_expect_tx(bar_ring_full(slot), bytes);
+                        mbar_expect_tx(bar_ring_full(slot), sbytes);
                         asm volatile(
                             "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
                                 ring0 + slot * slot_bytes),
-                            "l"(src), "r"(bytes), "r"(bar_ring_full(slot))
+                            "l"(src), "r"(sbytes), "r"(bar_ring_full(slot))
                             : "memory");
                         }
+                        src += sbytes - bytes;
                         src += bytes;
                         if (++slot == nslots) {
                             slot = 0;
@@ -679,6 +686,8 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         // warp 0 has issued iteration 0 (which overwrites the accumulator) both meet at a named barrier bracketed
         // by tcgen05 fences, so everything warp 1 issues is ordered after it.
         const int mw = (warp == 1) ? 0 : 1;
+        const bool two_issuers = (P.issuers == 2);
+        if (two_issuers || mw == 0) {
         // The whole warp runs this (warp-uniform) loop and only the tcgen05 instructions are
         // predicated on one elected lane: measured with tools/umma_probe.cu, a loop inside an
         // `if (lane == 0)` branch costs 269 cycles per MMA, this form 96..131.
@@ -731,9 +740,11 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 }
                 // chunk-start rendezvous of the two issuers: every MMA of earlier chunks (either warp) is ordered before
                 // the first MMA of this chunk, which may overwrite TMEM columns those MMAs read
-                tc_fence_before();
-                asm volatile("bar.sync 2, 64;\n" ::: "memory");
-                tc_fence_after();
+                if (two_issuers) {
+                    tc_fence_before();
+                    asm volatile("bar.sync 2, 64;\n" ::: "memory");
+                    tc_fence_after();
+                }
                 const uint32_t idesc = idesc_base | (static_cast<uint32_t>(C.ncols >> 3) << 17);
                 const uint32_t d = tm + static_cast<uint32_t>(C.dcol);
                 const uint32_t b_kg = static_cast<uint32_t>(C.ncols / CG) * 16u;  // bytes between B k-groups (this CTA's rows)
@@ -745,16 +756,18 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 uint32_t ta = tm;
                 const int nst = C.nstages;
                 int next_src_k = (src >= 0) ? 0 : 0x7fffffff;  // k-step at which the next producing chunk starts
-                for (int s = 0; s < nst; s += 2) {
-                    const bool two = (s + 1 < nst);
-                    // k-steps s (and s+1) may cross into the next chunk of the producing layer
-                    if (s + 1 >= next_src_k) {
+                const uint32_t kstep16 = b_kg * 4u >> 4;  // one k-step of this CTA's B rows ({hi, lo} tiles), 16 B units
+                for (int s = 0, it = 0; s < nst; s += 2 * KPS, ++it) {
+                    const int nk = min(2 * KPS, nst - s);  // k-steps of this iteration (two ring slots' worth)
+                    const bool two = (nk > KPS);           // second slot in use
+                    // the k-steps of this iteration may cross into the next chunk of the producing layer
+                    if (s + nk - 1 >= next_src_k) {
                         do {
                             const int j = src - P.L[C.layer - 1].first_chunk;
                             sync_event(bar_act_ready(j), (act_cnt[j]++) & 1u);
                             ++src;
                             next_src_k = (src < src_end) ? (P.C[src].n0 >> 4) : 0x7fffffff;
-                        } while (s + 1 >= next_src_k);
+                        } while (s + nk - 1 >= next_src_k);
                         tc_fence_after();
                     }
                     int slot1 = slot + 1;
@@ -764,7 +777,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                         ph1 ^= 1u;
                     }
                     const uint32_t full0 = bar0 + 8u * slot, full1 = bar0 + 8u * slot1;
-                    const bool mine = (((s >> 1) & 1) == mw);
+                    const bool mine = !two_issuers || ((it & 1) == mw);
                     if (!mine) {
                         // the other issuing warp handles this iteration
                     } else if (PAIR && !leader) {
@@ -778,89 +791,67 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                         __syncwarp();
                     } else {
                         // probe both stages' barriers back to back (their ~90-cycle latencies overlap)
-                        uint32_t ok = PAIR ? mbar_try_cluster(full0, rphase) : mbar_try(full0, rphase);
-                        if (two) ok &= PAIR ? mbar_try_cluster(full1, ph1) : mbar_try(full1, ph1);
+                        uint32_t ok = mbar_try(full0, rphase);
+                        if (two) ok &= mbar_try(full1, ph1);
                         if (!ok) {
-                            if (PAIR) {
-                                mbar_wait_cluster(full0, rphase);
-                                if (two) mbar_wait_cluster(full1, ph1);
-                            } else {
-                                mbar_wait(full0, rphase);
-                                if (two) mbar_wait(full1, ph1);
-                            }
+                            mbar_wait(full0, rphase);
+                            if (two) mbar_wait(full1, ph1);
                         }
                         tc_fence_after();
-                        const uint32_t b0 = b_base32 + slot * slot16, b1 = b_base32 + slot1 * slot16;
-                        const uint32_t acc0 = s > 0 ? 1u : 0u;
-                        const uint32_t a_lo = a_lo32 + ((2u * A_KG_BYTES) >> 4);
-                        const uint32_t a1 = a_lo32 + (KSTEP_BYTES >> 4), a1_lo = a_lo + (KSTEP_BYTES >> 4);
+                        const uint32_t bs0 = b_base32 + slot * slot16, bs1 = b_base32 + slot1 * slot16;
                         if (elect_one()) {
-                            if (DBG & 1) {
-                                if (PAIR) {
-                                    mma2_commit_both(full0 + 8u * MAX_SLOTS);
-                                    if (two) mma2_commit_both(full1 + 8u * MAX_SLOTS);
-                                } else {
-                                    mma_commit(full0 + 8u * MAX_SLOTS);
-                                    if (two) mma_commit(full1 + 8u * MAX_SLOTS);
-                                }
-                            } else if (PAIR) {
-                                if (ts) {
-                                    mma2_ts2(d, ta, b0, desc_hi, idesc, acc0);
-                                    mma2_ts2(d, ta, b0 + b_lo16, desc_hi, idesc, 1u);
-                                    mma2_ts2(d, ta + 8u, b0, desc_hi, idesc, 1u);
-                                } else {
-                                    mma2_ss2(d, a_lo32, b0, desc_hi, idesc, acc0);
-                                    mma2_ss2(d, a_lo32, b0 + b_lo16, desc_hi, idesc, 1u);
-                                    mma2_ss2(d, a_lo, b0, desc_hi, idesc, 1u);
-                                }
-                                mma2_commit_both(full0 + 8u * MAX_SLOTS);  // ring_empty(slot) in both CTAs
-                                if (two) {
-                                    if (ts) {
-                                        mma2_ts2(d, ta + 16u, b1, desc_hi, idesc, 1u);
-                                        mma2_ts2(d, ta + 16u, b1 + b_lo16, desc_hi, idesc, 1u);
-                                        mma2_ts2(d, ta + 24u, b1, desc_hi, idesc, 1u);
-                                    } else {
-                                        mma2_ss2(d, a1, b1, desc_hi, idesc, 1u);
-                                        mma2_ss2(d, a1, b1 + b_lo16, desc_hi, idesc, 1u);
-                                        mma2_ss2(d, a1_lo, b1, desc_hi, idesc, 1u);
+#pragma unroll
+                            for (int j = 0; j < 2 * KPS; ++j) {
+                                if (j < nk) {
+                                    const uint32_t bj = (j < KPS ? bs0 : bs1) + static_cast<uint32_t>(j % KPS) * kstep16;
+                                    const uint32_t acc0 = (s + j) > 0 ? 1u : 0u;
+                                    if (!(DBG & 1)) {
+                                        if (ts) {
+                                            const uint32_t taj = ta + 16u * j;
+                                            if (PAIR) {
+                                                mma2_ts2(d, taj, bj, desc_hi, idesc, acc0);
+                                                mma2_ts2(d, taj, bj + b_lo16, desc_hi, idesc, 1u);
+                                                mma2_ts2(d, taj + 8u, bj, desc_hi, idesc, 1u);
+                                            } else {
+                                                mma_ts2(d, taj, bj, desc_hi, idesc, acc0);
+                                                mma_ts2(d, taj, bj + b_lo16, desc_hi, idesc, 1u);
+                                                mma_ts2(d, taj + 8u, bj, desc_hi, idesc, 1u);
+                                            }
+                                        } else {
+                                            const uint32_t aj = a_lo32 + static_cast<uint32_t>(j) * (KSTEP_BYTES >> 4);
+                                            const uint32_t aj_lo = aj + ((2u * A_KG_BYTES) >> 4);
+                                            if (PAIR) {
+                                                mma2_ss2(d, aj, bj, desc_hi, idesc, acc0);
+                                                mma2_ss2(d, aj, bj + b_lo16, desc_hi, idesc, 1u);
+                                                mma2_ss2(d, aj_lo, bj, desc_hi, idesc, 1u);
+                                            } else {
+                                                mma_ss2(d, aj, bj, desc_hi, idesc, acc0);
+                                                mma_ss2(d, aj, bj + b_lo16, desc_hi, idesc, 1u);
+                                                mma_ss2(d, aj_lo, bj, desc_hi, idesc, 1u);
+                                            }
+                                        }
                                     }
-                                    mma2_commit_both(full1 + 8u * MAX_SLOTS);
-                                }
-                            } else {
-                                if (ts) {
-                                    mma_ts2(d, ta, b0, desc_hi, idesc, acc0);
-                                    mma_ts2(d, ta, b0 + b_lo16, desc_hi, idesc, 1u);
-                                    mma_ts2(d, ta + 8u, b0, desc_hi, idesc, 1u);
-                                } else {
-                                    mma_ss2(d, a_lo32, b0, desc_hi, idesc, acc0);
-                                    mma_ss2(d, a_lo32, b0 + b_lo16, desc_hi, idesc, 1u);
-                                    mma_ss2(d, a_lo, b0, desc_hi, idesc, 1u);
-                                }
-                                mma_commit(full0 + 8u * MAX_SLOTS);  // ring_empty(slot): frees the stage when read
-                                if (two) {
-                                    if (ts) {
-                                        mma_ts2(d, ta + 16u, b1, desc_hi, idesc, 1u);
-                                        mma_ts2(d, ta + 16u, b1 + b_lo16, desc_hi, idesc, 1u);
-                                        mma_ts2(d, ta + 24u, b1, desc_hi, idesc, 1u);
-                                    } else {
-                                        mma_ss2(d, a1, b1, desc_hi, idesc, 1u);
-                                        mma_ss2(d, a1, b1 + b_lo16, desc_hi, idesc, 1u);
-                                        mma_ss2(d, a1_lo, b1, desc_hi, idesc, 1u);
+                                    // last k-step of a slot: free it (in both CTAs of a pair) once these MMAs have read it
+                                    if (j == KPS - 1 || (j < KPS && j == nk - 1)) {
+                                        if (PAIR) mma2_commit_both(full0 + 8u * MAX_SLOTS);
+                                        else mma_commit(full0 + 8u * MAX_SLOTS);
+                                    } else if (j >= KPS && j == nk - 1) {
+                                        if (PAIR) mma2_commit_both(full1 + 8u * MAX_SLOTS);
+                                        else mma_commit(full1 + 8u * MAX_SLOTS);
                                     }
-                                    mma_commit(full1 + 8u * MAX_SLOTS);
                                 }
                             }
                         }
                         __syncwarp();
                     }
-                    if (s == 0) {
+                    if (s == 0 && two_issuers) {
                         // rendezvous of the two issuers: iteration 0 (accumulator overwrite) is issued, order the rest after it
                         tc_fence_before();
                         asm volatile("bar.sync 2, 64;\n" ::: "memory");
                         tc_fence_after();
                     }
-                    a_lo32 += 2 * (KSTEP_BYTES >> 4);
-                    ta += 32u;
+                    a_lo32 += static_cast<uint32_t>(2 * KPS) * (KSTEP_BYTES >> 4);
+                    ta += 32u * KPS;
                     slot += two ? 2 : 1;
                     if (slot >= nslots) {
                         slot -= nslots;
@@ -876,6 +867,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 }
                 ++seq;
             }
+        }
         }
         __syncwarp();
     } else {
