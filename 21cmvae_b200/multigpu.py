@@ -23,6 +23,31 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def bind_host_to_gpu(device_index: int) -> Optional[list]:
+    """Pin this process to the CPU cores NVML reports as local to GPU ``device_index`` (same NUMA node / PCIe
+    root), intersected with the cores the container allows.  Pinned host buffers allocated afterwards land on
+    that node, which matters for the PCIe-bound host<->device path when several ranks copy at once.
+    Returns the core list used, or None when NVML / affinity information is unavailable (no-op)."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        use = sorted(set(cores) & set(allowed))
+        if use:
+            os.sched_setaffinity(0, use)
+            return use
+    except Exception:  # noqa: BLE001 - affinity is an optimisation only
+        pass
+    return None
+
+
 def global_argmin(local_val: float, local_idx: int, row_offset: int, group=None) -> Tuple[float, int]:
     """Combine per-rank ``(min chi2, local row)`` into the global minimum and GLOBAL row index.
     One all_gather of 16 bytes per rank.  NaN / idx < 0 (no finite value on a rank) never wins."""

@@ -220,6 +220,8 @@ def main():
     pp = importlib.import_module("21cmvae_b200.preprocess")
     kh = importlib.import_module("21cmvae_b200.keras_h5")
     L = importlib.import_module("21cmvae_b200._lib")
+    mg = importlib.import_module("21cmvae_b200.multigpu")
+    numa_cores = mg.bind_host_to_gpu(local) if world > 1 else None  # keep pinned buffers on the GPU's NUMA node
 
     rm, ks, bs, relu, mu, sd, pmin, pmax, params = build_problem(args.rows, 20220322 + rank)
     emu = emu_mod.DirectEmulator(stats=pp.NormStats(pmin, pmax, mu, sd), device=local)
@@ -337,7 +339,7 @@ def main():
             "config": {"workload": "DirectEmulator.predict 7->288->352->288->224->451, full 451-bin output to HBM",
                        "rows_per_gpu": n, "params_dtype": "f64", "precision_path": prec_name,
                        "weights": "random-init (Glorot), shipped emulator.h5 absent from the reference checkout",
-                       "l2": "working set 1.86 GB/step >> 126 MB L2 (no flush needed)", "parallelism": f"rows sharded x{world}"},
+                       "l2": "working set 1.86 GB/step >> 126 MB L2 (no flush needed)", "parallelism": f"rows sharded x{world}", "host_cores_bound": (len(numa_cores) if numa_cores else None)},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * 56, "d2h_bytes_per_step": n * 1804,
                     "steps": e2e_steps, "checksum": checksum},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,

@@ -283,3 +283,30 @@ def test_tc_deterministic_mode_is_bitwise_reproducible(rm, direct_fixture):
     outs = [subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300).stdout.strip()
             for _ in range(2)]
     assert outs[0] == outs[1] and outs[0] != "DIFF" and len(outs[0]) == 64, outs
+
+
+def test_autoencoder_emulator_end_to_end_from_h5(tmp_path, rm, ae_golden):
+    """AutoEncoderEmulator (emulator.py:770-795): two Keras files -> one fused chain, real trained weights."""
+    emu = pkg("emulator")
+    pp = pkg("preprocess")
+    kh = pkg("keras_h5")
+    g = ae_golden
+    em = kh.DenseChainWeights(g["kernels"][:5], g["biases"][:5], g["relu"][:5], name="AE_Emulator")
+    de = kh.DenseChainWeights(g["kernels"][5:], g["biases"][5:], g["relu"][5:], name="Decoder")
+    kh.save_dense_chain(str(tmp_path / "ae_emulator.h5"), em)
+    kh.save_dense_chain(str(tmp_path / "decoder.h5"), de)
+    pmin, pmax = rm.prior_par_stats()
+    mu = np.linspace(-120, 10, 451).astype(np.float32)
+    sd = np.float32(47.5)
+    ae = emu.AutoEncoderEmulator(stats=pp.NormStats(pmin, pmax, mu, sd))
+    ae.load_model(str(tmp_path / "ae_emulator.h5"), str(tmp_path / "decoder.h5"))
+    p = rm.draw_params(333, seed=21)
+    want = rm.predict(p, g["kernels"], g["biases"], g["relu"], pmin, pmax, mu, sd)
+    got = ae.predict(p)
+    assert got.shape == (333, 451) and _rel_err(got, want) <= FP32_TOL
+    assert ae.predict(p[0]).shape == (451,)
+    # latent head alone (what the reference's self.emulator.predict returns)
+    x = rm.par_transform_cached(p, pmin, pmax).astype(np.float32)
+    lat = ae.emulator.predict(x)
+    assert lat.shape == (333, 9)
+    assert np.allclose(lat, rm.dense_chain(x, g["kernels"][:5], g["biases"][:5], g["relu"][:5]), atol=2e-5)
