@@ -316,6 +316,8 @@ def main():
             roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": ach / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " (burst, cuBLAS bf16)",
                     "frac_executed": per_gpu_rate * 2 * EXEC_MAC_PER_SIGNAL_TC / 1e12 / pk["bf16_tflops"],
+                    "frac_executed_of_sustained": (per_gpu_rate * 2 * EXEC_MAC_PER_SIGNAL_TC / 1e12 / pk["bf16_tflops_sustained"]
+                                                   if pk.get("bf16_tflops_sustained") else None),
                     "hbm_gbs_achieved": per_gpu_rate * BYTES_PER_SIGNAL_F64 / 1e9,
                     "note": "achieved = algorithmic 740,608 FLOP/signal; frac_executed counts the 3 split passes "
                             "and MMA-shape padding actually issued to the tensor pipe"}
