@@ -36,8 +36,12 @@
 namespace tck {
 
 constexpr int MT = 128;
-constexpr int NTHREADS = 352;   // warp 0 producer, warps 1 and 10 MMA issuers, warps 2..9 epilogue
-constexpr int NEPI = 256;       // epilogue threads
+#ifndef VAE21_TC_EPI_PER_SUB
+#define VAE21_TC_EPI_PER_SUB 4   // epilogue warps per TMEM sub-partition (2, 3 or 4): 4 measured best (1.95 vs 1.99 ms)
+#endif
+constexpr int EPS = VAE21_TC_EPI_PER_SUB;
+constexpr int NEPI = 128 * EPS;          // epilogue threads
+constexpr int NTHREADS = 128 + NEPI;     // warp 0 producer, warps 1 and 2 MMA issuers, warp 3 idle, warps 4.. epilogue
 constexpr int MAXL = 8;
 constexpr int MAXC = 32;
 constexpr int NFULL = 4;          // ring of "accumulator chunk ready" barriers
@@ -45,6 +49,12 @@ constexpr int NFULL = 4;          // ring of "accumulator chunk ready" barriers
 #define VAE21_TC_ABLATE 0  // profiling only: 1 no MMA issue, 2 no epilogue work, 4 no weight copies (bit mask)
 #endif
 constexpr int DBG = VAE21_TC_ABLATE;
+#ifndef VAE21_TC_TIMING
+#define VAE21_TC_TIMING 0  // profiling only: per-CTA cycle counters of the first MMA warp's waits
+#endif
+#if VAE21_TC_TIMING
+__device__ long long g_tc_timing[160][16];  // [cta][0 total, 1..5 operand-ready wait by consuming layer, 6..10 q_empty wait by layer, 11 ring, 12 rendezvous, 13 issue]
+#endif
 constexpr int MAX_SLOTS = 8;
 constexpr int MAX_LCHUNK = 4;      // chunks per non-final layer (per-chunk operand-ready barriers)
 constexpr int SMEM_LIMIT = 227 * 1024;
@@ -245,7 +255,7 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
     // shared memory
     int off = 0;
     P.off_act = off;
-    const int stage_bytes = 8 * 32 * 20 * 4;  // output transpose staging of the 8 epilogue warps
+    const int stage_bytes = 4 * EPS * 32 * 20 * 4;  // output transpose staging of the epilogue warps
     int act_bytes = std::max(smem_w / 16 * KSTEP_BYTES, stage_bytes);
     // The staging tiles alias the activation buffer where the last layer does not read it: all of it when
     // the last layer's operand is in TMEM, else the part above that operand (grown if needed).
@@ -269,7 +279,7 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
     P.off_isig = off;
     off += nop * 4;
     P.off_bar = off;
-    off += 256 + 2 * 16 * 4 + 2 * 128 * 4;  // barriers + prologue constants + chi^2 partials
+    off += 256 + 2 * 16 * 4 + 2 * (EPS - 1) * 128 * 4;  // barriers + prologue constants + chi^2 partials
     off = (off + 127) / 128 * 128;
     P.off_ring = off;
     const int avail = SMEM_LIMIT - 128 /*alignment slack*/ - off;
@@ -580,7 +590,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + P.off_bar + 8 * (2 * MAX_SLOTS + NFULL + 3 + MAX_LCHUNK));
     float* s_pmin = reinterpret_cast<float*>(sm + P.off_bar + 256);   // [16] fp32 copies of the prologue constants
     float* s_pscale = s_pmin + 16;                                    // [16] 2 / (pmax - pmin)
-    float* s_chi = s_pscale + 16;                                     // [2][128] chi^2 partials of the second column half
+    float* s_chi = s_pscale + 16;                                     // [2][EPS-1][128] chi^2 partials of the other column shares
 
     float* s_bias = reinterpret_cast<float*>(sm + P.off_bias);
     float* s_s0 = reinterpret_cast<float*>(sm + P.off_s0);
@@ -596,10 +606,11 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         }
         const uint32_t fwd = (PAIR && leader) ? 1u : 0u;  // + one forwarded arrival from the peer CTA
         for (int i = 0; i < NFULL; ++i) mbar_init(bar_chunk_full(i), P.issuers);
-        for (int b = 0; b < 2; ++b) mbar_init(bar_q_empty(b), NEPI + fwd);
+        // epilogue -> MMA hand-offs: ONE arrival per epilogue warp (elected lane after __syncwarp), not one per thread
+        for (int b = 0; b < 2; ++b) mbar_init(bar_q_empty(b), NEPI / 32 + fwd);
         // (chunk_full: one commit from each of the two issuing warps)
-        for (int j = 0; j < MAX_LCHUNK; ++j) mbar_init(bar_act_ready(j), NEPI + fwd);
-        mbar_init(bar_a0_ready, 128 + fwd);
+        for (int j = 0; j < MAX_LCHUNK; ++j) mbar_init(bar_act_ready(j), NEPI / 32 + fwd);
+        mbar_init(bar_a0_ready, 4 + fwd);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (tid < 16) {
@@ -678,14 +689,14 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 }
             }
         }
-    } else if (warp == 1 || warp == 10) {
+    } else if (warp == 1 || warp == 2) {
         // ===================== MMA issuers ===================================================
         // Two warps share the issue work (one warp alone is the limiter: ~100 instructions per 6 MMAs at the
         // latency-bound rate of a lone warp).  Within an accumulator chunk warp mw issues the pair-iterations
         // with (iteration & 1) == mw.  Ordering between the two issuers is established once per chunk: after
         // warp 0 has issued iteration 0 (which overwrites the accumulator) both meet at a named barrier bracketed
         // by tcgen05 fences, so everything warp 1 issues is ordered after it.
-        const int mw = (warp == 1) ? 0 : 1;
+        const int mw = warp - 1;
         const bool two_issuers = (P.issuers == 2);
         if (two_issuers || mw == 0) {
         // The whole warp runs this (warp-uniform) loop and only the tcgen05 instructions are
@@ -705,6 +716,14 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         // In the CTA-pair kernel rank 0 issues; rank 1 runs the SAME schedule as a forwarder: wherever the
         // issuer waits for an event, the forwarder waits for its own CTA's instance of it and then arrives on
         // the issuer's barrier (which counts the local arrivals plus this one).
+#if VAE21_TC_TIMING
+        long long tm_total = clock64(), tm_evt[5] = {0, 0, 0, 0, 0}, tm_q[5] = {0, 0, 0, 0, 0}, tm_ring = 0, tm_rdv = 0, tm_issue = 0, tm_setup = 0, tm_it_mine = 0, tm_it_other = 0;
+#define TSTART const long long t_s_ = clock64();
+#define TADD(var) var += clock64() - t_s_;
+#else
+#define TSTART
+#define TADD(var)
+#endif
         auto sync_event = [&](uint32_t bar, uint32_t parity) {
             if (!PAIR) {
                 mbar_wait(bar, parity);
@@ -718,6 +737,9 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         };
         for (long long unit = unit0; unit < nunits; unit += ustep) {
             for (int c = 0; c < n_chunks; ++c) {
+#if VAE21_TC_TIMING
+                const long long t_chunk0 = clock64();
+#endif
                 const Chunk& C = P.C[c];
                 const Layer& L = P.L[C.layer];
                 // Operand readiness is tracked per chunk of the PRODUCING layer: k-step s of this layer only needs
@@ -726,7 +748,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 int src = -1, src_end = -1;  // chunks of the producing layer still to wait for
                 if (c == L.first_chunk) {
                     if (C.layer == 0) {
-                        sync_event(bar_a0_ready, a0_cnt & 1u);
+                        { TSTART sync_event(bar_a0_ready, a0_cnt & 1u); TADD(tm_evt[0]) }
                         ++a0_cnt;
                     } else {
                         src = P.L[C.layer - 1].first_chunk;
@@ -736,14 +758,16 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 if (C.qbuf >= 0) {  // accumulator buffer must have been drained by the epilogue
                     const uint32_t u = C.qbuf ? q_use1 : q_use0;
                     if (C.qbuf) ++q_use1; else ++q_use0;
-                    if (u > 0) sync_event(bar_q_empty(C.qbuf), (u - 1u) & 1u);
+                    if (u > 0) { TSTART sync_event(bar_q_empty(C.qbuf), (u - 1u) & 1u); TADD(tm_q[C.layer < 5 ? C.layer : 4]) }
                 }
                 // chunk-start rendezvous of the two issuers: every MMA of earlier chunks (either warp) is ordered before
                 // the first MMA of this chunk, which may overwrite TMEM columns those MMAs read
                 if (two_issuers) {
+                    TSTART
                     tc_fence_before();
                     asm volatile("bar.sync 2, 64;\n" ::: "memory");
                     tc_fence_after();
+                    TADD(tm_rdv)
                 }
                 const uint32_t idesc = idesc_base | (static_cast<uint32_t>(C.ncols >> 3) << 17);
                 const uint32_t d = tm + static_cast<uint32_t>(C.dcol);
@@ -757,14 +781,20 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 const int nst = C.nstages;
                 int next_src_k = (src >= 0) ? 0 : 0x7fffffff;  // k-step at which the next producing chunk starts
                 const uint32_t kstep16 = b_kg * 4u >> 4;  // one k-step of this CTA's B rows ({hi, lo} tiles), 16 B units
+#if VAE21_TC_TIMING
+                tm_setup += clock64() - t_chunk0;
+#endif
                 for (int s = 0, it = 0; s < nst; s += 2 * KPS, ++it) {
+#if VAE21_TC_TIMING
+                    const long long t_it0 = clock64();
+#endif
                     const int nk = min(2 * KPS, nst - s);  // k-steps of this iteration (two ring slots' worth)
                     const bool two = (nk > KPS);           // second slot in use
                     // the k-steps of this iteration may cross into the next chunk of the producing layer
                     if (s + nk - 1 >= next_src_k) {
                         do {
                             const int j = src - P.L[C.layer - 1].first_chunk;
-                            sync_event(bar_act_ready(j), (act_cnt[j]++) & 1u);
+                            { TSTART sync_event(bar_act_ready(j), (act_cnt[j]++) & 1u); TADD(tm_evt[C.layer < 5 ? C.layer : 4]) }
                             ++src;
                             next_src_k = (src < src_end) ? (P.C[src].n0 >> 4) : 0x7fffffff;
                         } while (s + nk - 1 >= next_src_k);
@@ -791,13 +821,20 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                         __syncwarp();
                     } else {
                         // probe both stages' barriers back to back (their ~90-cycle latencies overlap)
-                        uint32_t ok = mbar_try(full0, rphase);
-                        if (two) ok &= mbar_try(full1, ph1);
-                        if (!ok) {
-                            mbar_wait(full0, rphase);
-                            if (two) mbar_wait(full1, ph1);
+                        {
+                            TSTART
+                            uint32_t ok = mbar_try(full0, rphase);
+                            if (two) ok &= mbar_try(full1, ph1);
+                            if (!ok) {
+                                mbar_wait(full0, rphase);
+                                if (two) mbar_wait(full1, ph1);
+                            }
+                            TADD(tm_ring)
                         }
                         tc_fence_after();
+#if VAE21_TC_TIMING
+                        const long long t_issue0 = clock64();
+#endif
                         const uint32_t bs0 = b_base32 + slot * slot16, bs1 = b_base32 + slot1 * slot16;
                         if (elect_one()) {
 #pragma unroll
@@ -843,12 +880,17 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                             }
                         }
                         __syncwarp();
+#if VAE21_TC_TIMING
+                        tm_issue += clock64() - t_issue0;
+#endif
                     }
                     if (s == 0 && two_issuers) {
+                        TSTART
                         // rendezvous of the two issuers: iteration 0 (accumulator overwrite) is issued, order the rest after it
                         tc_fence_before();
                         asm volatile("bar.sync 2, 64;\n" ::: "memory");
                         tc_fence_after();
+                        TADD(tm_rdv)
                     }
                     a_lo32 += static_cast<uint32_t>(2 * KPS) * (KSTEP_BYTES >> 4);
                     ta += 32u * KPS;
@@ -857,6 +899,9 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                         slot -= nslots;
                         rphase ^= 1u;
                     }
+#if VAE21_TC_TIMING
+                    if (mine) tm_it_mine += clock64() - t_it0; else tm_it_other += clock64() - t_it0;
+#endif
                 }
                 if (!PAIR || leader) {
                     if (elect_one()) {
@@ -868,14 +913,22 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 ++seq;
             }
         }
+#if VAE21_TC_TIMING
+        if (mw == 0 && lane == 0 && blockIdx.x < 160) {
+            long long* o = g_tc_timing[blockIdx.x];
+            o[0] = clock64() - tm_total;
+            for (int i = 0; i < 5; ++i) { o[1 + i] = tm_evt[i]; o[6 + i] = tm_q[i]; }
+            o[11] = tm_ring; o[12] = tm_rdv; o[13] = tm_issue; o[14] = tm_setup; o[15] = tm_it_mine;
+        }
+#endif
         }
         __syncwarp();
-    } else {
+    } else if (warp >= 4) {
         // ===================== epilogue warps ================================================
         // thread = tile row = TMEM lane; the two warps that share a TMEM sub-partition split the
         // 16-column groups of every accumulator chunk (even / odd groups).
-        const int ew = warp - 2;
-        const int half = ew >> 2;                 // 0: even groups (+ the prologue), 1: odd groups
+        const int ew = warp - 4;
+        const int half = ew >> 2;                 // which share of the 16-column groups (0 also does the prologue)
         const int sub = warp & 3;                 // TMEM sub-partition this warp may access
         const int row = sub * 32 + lane;          // tile row == TMEM lane
         const uint32_t tlane = static_cast<uint32_t>(sub * 32) << 16;
@@ -925,7 +978,8 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             *reinterpret_cast<uint4*>(a0 + 2 * A_KG_BYTES + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             *reinterpret_cast<uint4*>(a0 + 3 * A_KG_BYTES + row * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
             fence_async_smem();
-            mbar_arrive(bar_a0_ready);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a0_ready);
         };
 
         if (half == 0 && unit0 < nunits) write_a0(CG * unit0 + rank);
@@ -1026,14 +1080,14 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 if (half < ng && !(DBG & 2)) {
                     uint32_t ra[16], rb[16];
                     tmem_ld16(tbase + static_cast<uint32_t>(16 * half), ra);
-                    for (int g = half; g < ng; g += 4) {
+                    for (int g = half; g < ng; g += 2 * EPS) {
                         tmem_ld_wait();
-                        if (g + 2 < ng) tmem_ld16(tbase + static_cast<uint32_t>(16 * (g + 2)), rb);
+                        if (g + EPS < ng) tmem_ld16(tbase + static_cast<uint32_t>(16 * (g + EPS)), rb);
                         process(ra, g);
-                        if (g + 2 < ng) {
+                        if (g + EPS < ng) {
                             tmem_ld_wait();
-                            if (g + 4 < ng) tmem_ld16(tbase + static_cast<uint32_t>(16 * (g + 4)), ra);
-                            process(rb, g + 2);
+                            if (g + 2 * EPS < ng) tmem_ld16(tbase + static_cast<uint32_t>(16 * (g + 2 * EPS)), ra);
+                            process(rb, g + EPS);
                         }
                     }
                 }
@@ -1041,9 +1095,12 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 if (out_dst == DST_SMEM) fence_async_smem();
                 if (out_dst == DST_TMEM) tmem_st_wait();
                 tc_fence_before();
-                if (C.qbuf >= 0) mbar_arrive(bar_q_empty(C.qbuf));
+                __syncwarp();  // every lane's writes / reads are done and fenced before the elected lane signals
+                if (lane == 0) {
+                    if (C.qbuf >= 0) mbar_arrive(bar_q_empty(C.qbuf));
+                    if (out_dst != DST_FINAL) mbar_arrive(bar_act_ready(c - L.first_chunk));
+                }
                 const bool last_of_layer = (c == L.first_chunk + L.nchunks - 1);
-                if (out_dst != DST_FINAL) mbar_arrive(bar_act_ready(c - L.first_chunk));
                 // the layer-0 operand of the NEXT tile can be written as soon as layer 0 of this tile is done
                 if (half == 0 && C.layer == 0 && last_of_layer) {
                     if (unit + ustep < nunits) write_a0(CG * (unit + ustep) + rank);
@@ -1051,11 +1108,12 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             }
             // tile end: all epilogue warps meet (the output staging tiles alias the activation buffer, and the
             // two column halves of a row combine their chi^2 partials here)
-            float* chi_buf = s_chi + (tcount & 1u) * 128;
-            if (a.out_mode == OUT_CHI2 && half == 1) chi_buf[row] = chi;
+            float* chi_buf = s_chi + (tcount & 1u) * (EPS - 1) * 128;
+            if (a.out_mode == OUT_CHI2 && half > 0) chi_buf[(half - 1) * 128 + row] = chi;
             asm volatile("bar.sync 1, %0;\n" ::"n"(NEPI) : "memory");
             if (a.out_mode == OUT_CHI2 && half == 0) {
-                chi += chi_buf[row];
+#pragma unroll
+                for (int hh = 0; hh < EPS - 1; ++hh) chi += chi_buf[hh * 128 + row];
                 unsigned long long key = ~0ull;
                 if (grow < a.n) {
                     if (a.chi2) a.chi2[grow] = chi;
@@ -1126,5 +1184,9 @@ inline cudaError_t launch(const Plan& P, const NormConsts& nc, const LaunchArgs&
     const int grid = static_cast<int>(std::min<long long>(ntiles, sm_count));
     return fmt == 0 ? launch_one<0, 1>(P, nc, a, w, bias, grid, st) : launch_one<1, 1>(P, nc, a, w, bias, grid, st);
 }
+
+#if VAE21_TC_TIMING
+inline cudaError_t read_timing(long long* host /*[160*16]*/) { return cudaMemcpyFromSymbol(host, g_tc_timing, sizeof(long long) * 160 * 16); }
+#endif
 
 }  // namespace tck
