@@ -181,11 +181,34 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Keep stdout clean for the ONE JSON line: libraries (NCCL's version banner, torchrun notices) write to
+    fd 1 too, so fd 1 is pointed at stderr for the rest of the run and the result goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -347,7 +370,7 @@ def main():
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "check": {"max_abs_err_mK": max_mk, "max_err_over_amplitude": rel, "rows_checked": int(len(idx))},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
