@@ -131,9 +131,10 @@ inline float h162f(unsigned short u) {
 }
 
 // Build the schedule for a Dense stack.  Returns false (with `why`) when the stack does not fit.
-inline bool build_plan(int n_layers, const int* dims, const float* const* kernels, const float* const* biases,
-                       const int* relu, Plan& P, std::vector<unsigned short>* img /*[2]: bf16, fp16*/,
-                       std::vector<float>& bias_img, std::string& why) {
+inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, const float* const* kernels,
+                            const float* const* biases, const int* relu, Plan& P,
+                            std::vector<unsigned short>* img /*[2]: bf16, fp16*/, std::vector<float>& bias_img,
+                            std::string& why) {
     P = Plan{};
     if (n_layers < 2 || n_layers > MAXL) { why = "needs 2.." + std::to_string(MAXL) + " layers"; return false; }
     if (relu[n_layers - 1]) { why = "last layer must be linear"; return false; }
@@ -169,7 +170,7 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
         if (l == n_layers - 1) {
             L.out_dst = DST_FINAL;
         } else if (L.a_src == A_SMEM_A0) {
-            L.out_dst = DST_SMEM;
+            L.out_dst = first_to_tmem ? DST_TMEM : DST_SMEM;  // the parity of the whole chain (see build_plan)
         } else if (L.a_src == A_SMEM_ACT) {
             L.out_dst = (L.Npad <= 224 && l == n_layers - 2 && std::getenv("VAE21_TC_SS_LAST")) ? DST_SMEM : DST_TMEM;
         } else {
@@ -290,6 +291,10 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
     P.slot_bytes2 = P.slot_bytes;
     P.nslots2 = std::min(MAX_SLOTS, avail / P.slot_bytes2) & ~1;  // even: the MMA loop consumes slots in pairs
     P.smem_total2 = off + P.nslots2 * P.slot_bytes2 + 128;
+    // Two issuing warps alternate loop iterations of two slots each.  mbarrier waits are by phase PARITY, so each
+    // issuer must observe every ring cycle at least once: with fewer than 4 slots (one iteration per cycle) an issuer
+    // would skip every other phase of its slots and pass its wait on a stale completion.  Use one issuer then.
+    if (std::min(P.nslots, P.nslots2) < 4) P.issuers = 1;
     off += P.nslots * P.slot_bytes;
     P.smem_total = off + 128;
 
@@ -337,6 +342,33 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
     for (int l = 0; l < n_layers; ++l)
         for (int n = 0; n < dims[l + 1]; ++n) bias_img[P.L[l].bias_off + n] = biases[l][n];
     return true;
+}
+
+// Activations alternate shared memory / TMEM along the chain; which of the two the FIRST hidden layer uses
+// decides where the wide layers land.  Try "h1 in shared memory" (best for the DirectEmulator stack), and
+// fall back to "h1 in TMEM" (the AE chain: its 352-wide layers then fit, and its last layer reads TMEM so
+// the output staging can alias the activation buffer).  Keep the variant with the deeper weight ring.
+inline bool build_plan(int n_layers, const int* dims, const float* const* kernels, const float* const* biases,
+                       const int* relu, Plan& P, std::vector<unsigned short>* img, std::vector<float>& bias_img,
+                       std::string& why) {
+    std::string why_a, why_b;
+    if (build_plan_with(false, n_layers, dims, kernels, biases, relu, P, img, bias_img, why_a) && P.nslots >= 3) return true;
+    Plan Pa = P;
+    const bool ok_a = why_a.empty() && Pa.n_chunks > 0 && Pa.nslots >= 2;
+    std::vector<unsigned short> img_b[2];
+    std::vector<float> bias_b;
+    Plan Pb;
+    const bool ok_b = build_plan_with(true, n_layers, dims, kernels, biases, relu, Pb, img_b, bias_b, why_b);
+    if (ok_b && (!ok_a || Pb.nslots > Pa.nslots)) {
+        P = Pb;
+        img[0].swap(img_b[0]);
+        img[1].swap(img_b[1]);
+        bias_img.swap(bias_b);
+        return true;
+    }
+    if (ok_a) return build_plan_with(false, n_layers, dims, kernels, biases, relu, P, img, bias_img, why_a);
+    why = why_a.empty() ? why_b : why_a;
+    return false;
 }
 
 // ---------------------------------------------------------------------------------------------
