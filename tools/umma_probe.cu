@@ -360,15 +360,16 @@ time_kernel3(int N, int a_tmem, int nmma, long long* out) {
     if (warp == 0) {
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t sA = smem_u32(smem), sB = smem_u32(smem) + 16384;
-        const uint64_t da = make_desc(sA, 2048, 128);
-        const uint64_t db = make_desc(sB, (uint32_t)N * 16, 128);
+        // SAME == 2: 128-byte-swizzled K-major operands (8-row x 128 B atoms, SBO = 1024 B), k-steps 32 B apart
+        const uint64_t da = SAME == 2 ? (make_desc(sA, 16, 1024) | (2ull << 61)) : make_desc(sA, 2048, 128);
+        const uint64_t db = SAME == 2 ? (make_desc(sB, 16, 1024) | (2ull << 61)) : make_desc(sB, (uint32_t)N * 16, 128);
         const long long t0 = clock64();
         for (int i = 0; i < nmma; i += G) {
             if (elect_one()) {
 #pragma unroll
                 for (int u = 0; u < G; ++u) {
-                    const uint64_t dbi = SAME ? db : db + (uint64_t)(u * 64);
-                    const uint64_t dai = SAME ? da : da + (uint64_t)(u * 16);
+                    const uint64_t dbi = SAME == 1 ? db : (SAME == 2 ? db + (uint64_t)((u & 3) * 2) : db + (uint64_t)(u * 64));
+                    const uint64_t dai = SAME == 1 ? da : (SAME == 2 ? da + (uint64_t)((u & 3) * 2) : da + (uint64_t)(u * 16));
                     if (a_tmem)
                         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tm),
                                      "r"(tm + 480u), "l"(dbi), "r"(idesc), "r"(1u) : "memory");
@@ -420,7 +421,7 @@ static int run_timing(int argc, char** argv) {
     if (argv[1][1] == '3') {
         for (int N : {64, 144, 240})
             for (int at = 0; at < 2; ++at) {
-                run3<1, 0>(N, at, d); run3<3, 0>(N, at, d); run3<6, 0>(N, at, d); run3<12, 0>(N, at, d); run3<6, 1>(N, at, d);
+                run3<1, 0>(N, at, d); run3<3, 0>(N, at, d); run3<6, 0>(N, at, d); run3<12, 0>(N, at, d); run3<6, 1>(N, at, d); run3<6, 2>(N, at, d);
             }
         return 0;
     }
