@@ -9,9 +9,9 @@
 //   ping-pong buffers (even / odd layer inputs);
 //   weights stream from global/L2 through a cp.async ring of [KB][Npad] fp32 stages
 //   (host-packed, zero padded: Kpad % 8 == 0, Npad % 32 == 0);
-//   warp w owns rows 8w..8w+7 of the tile; lane t owns columns t, t+32, ... (TN of them):
-//   per k a thread does 2 broadcast LDS.128 (its 8 rows) + TN conflict-free LDS.32 and
-//   8*TN FFMA.
+//   warp w owns rows 8w..8w+7 of the tile; lane t owns TN columns: 4 consecutive ones in each leading
+//   128-column block (one LDS.128 per k) plus one per remaining 32-column slot:
+//   per k a thread does 2 broadcast LDS.128 (its 8 rows) + TN/4 LDS.128 + (TN%4) LDS.32 and 8*TN FFMA.
 #pragma once
 #include "common.cuh"
 
@@ -57,6 +57,11 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
     const int nkb = L.Kpad / KB;
     const int chunks = (KB * Npad) >> 2;  // 16-byte chunks per stage
 
+    // Column ownership of a lane: the first NQ*128 columns in "quads" (4 consecutive columns, one LDS.128 per k),
+    // the remaining NS 32-column slots one column each.  Slot j of the accumulator array is column col_of(j).
+    constexpr int NQ = TN >> 2, NS = TN & 3;
+    auto col_of = [&](int j) { return j < 4 * NQ ? 128 * (j >> 2) + 4 * lane + (j & 3) : 128 * NQ + 32 * (j - 4 * NQ) + lane; };
+
     float acc[8][TN];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -80,16 +85,27 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
         const int nxt = kb + WST - 1;
         if (nxt < nkb) load_stage(nxt, nxt % WST);
         cp_async_commit();
-        const float* ws = wst + (kb % WST) * stage_floats + lane;
+        const float* ws = wst + (kb % WST) * stage_floats;
         const float* ap = in + (kb * KB) * LDA + 8 * warp;
 #pragma unroll
         for (int kk = 0; kk < KB; ++kk) {
             const float4 a0 = *reinterpret_cast<const float4*>(ap + kk * LDA);
             const float4 a1 = *reinterpret_cast<const float4*>(ap + kk * LDA + 4);
             const float* wk = ws + kk * Npad;
+            float wv[TN];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wk + 128 * q + 4 * lane);
+                wv[4 * q + 0] = w4.x;
+                wv[4 * q + 1] = w4.y;
+                wv[4 * q + 2] = w4.z;
+                wv[4 * q + 3] = w4.w;
+            }
+#pragma unroll
+            for (int sgl = 0; sgl < NS; ++sgl) wv[4 * NQ + sgl] = wk[128 * NQ + 32 * sgl + lane];
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
-                const float w = wk[32 * j];
+                const float w = wv[j];
                 acc[0][j] = fmaf(a0.x, w, acc[0][j]);
                 acc[1][j] = fmaf(a0.y, w, acc[1][j]);
                 acc[2][j] = fmaf(a0.z, w, acc[2][j]);
@@ -106,7 +122,7 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
     if (!last) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-            const int n = lane + 32 * j;
+            const int n = col_of(j);
             const float b = __ldg(Bl + n);
             float v[8];
 #pragma unroll
@@ -127,7 +143,7 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
             for (int i = 0; i < 8; ++i) part[i] = 0.f;
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
-                const int n = lane + 32 * j;
+                const int n = col_of(j);
                 if (n < N) {
                     const float b = __ldg(Bl + n), mu = __ldg(a.mu + n), ob = __ldg(a.obs + n), is = __ldg(a.isig + n);
 #pragma unroll
@@ -156,7 +172,7 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
             const bool denorm = (a.out_mode == OUT_PREDICT);
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
-                const int n = lane + 32 * j;
+                const int n = col_of(j);
                 if (n < N) {
                     const float b = __ldg(Bl + n);
                     const float mu = denorm ? __ldg(a.mu + n) : 0.f;

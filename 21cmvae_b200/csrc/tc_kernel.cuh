@@ -93,8 +93,6 @@ struct Plan {
     int smem_total2;
     int default_cg;              // kernel variant used unless VAE21_TC_CTA_GROUP overrides it
     int issuers;                 // MMA-issuing warps: 2 (default) or 1 (VAE21_TC_DETERMINISTIC=1: bitwise reproducible sums)
-    int lookahead;  // (unused experiment flag)
-    int dbg;        // ablation bits for profiling (VAE21_TC_DEBUG): 1 no MMA issue, 2 no epilogue work, 4 no weight copies
     int bias_total;
     // shared-memory carve-up (bytes from the 1024-aligned base)
     int off_act, off_stage, off_a0, off_ring, off_bias, off_s0, off_obs, off_isig, off_bar, smem_total;
@@ -140,10 +138,8 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
     if (relu[n_layers - 1]) { why = "last layer must be linear"; return false; }
     if (dims[0] > 16) { why = "more than 16 input parameters"; return false; }
     P.n_layers = n_layers;
-    P.lookahead = std::getenv("VAE21_TC_LOOKAHEAD") ? 1 : 0;  // measured slower (2.87 vs 2.72 ms): off by default
     P.default_cg = 2;
     P.issuers = std::getenv("VAE21_TC_DETERMINISTIC") ? 1 : 2;
-    P.dbg = std::getenv("VAE21_TC_DEBUG") ? std::atoi(std::getenv("VAE21_TC_DEBUG")) : 0;
     P.K0 = dims[0];
     P.n_out = dims[n_layers];
     auto pad16 = [](int x) { return (x + 15) / 16 * 16; };
@@ -609,7 +605,6 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     // work units: 128-row tiles (CG 1) or 256-row super-tiles (CG 2); this CTA's tile of unit u is CG*u + rank
     const long long nunits = (a.n + CG * MT - 1) / (CG * MT);
     const long long unit0 = blockIdx.x / CG, ustep = gridDim.x / CG;
-    const long long ntiles = nunits;  // (loop bound below)
 
     // barrier addresses
     const uint32_t bar0 = base + P.off_bar;

@@ -310,3 +310,26 @@ def test_autoencoder_emulator_end_to_end_from_h5(tmp_path, rm, ae_golden):
     lat = ae.emulator.predict(x)
     assert lat.shape == (333, 9)
     assert np.allclose(lat, rm.dense_chain(x, g["kernels"][:5], g["biases"][:5], g["relu"][:5]), atol=2e-5)
+
+
+def test_time_predict_and_pinned_pool(rm, direct_fixture, emu_direct):
+    """vae21_time_predict (device-timed back-to-back launches) and the pinned host pool."""
+    import torch
+
+    L = pkg("_lib")
+    h = emu_direct._handle()
+    p = torch.from_numpy(rm.draw_params(50_000, seed=2)).cuda()
+    o = torch.empty((50_000, 451), dtype=torch.float32, device="cuda")
+    ms = h.time_predict(p, o, precision=L.FP32_SIMT, iters=3)
+    assert 0 < ms < 100
+    want = _oracle(rm, direct_fixture, p[:64].cpu().numpy())
+    assert _rel_err(o[:64].cpu().numpy(), want) <= FP32_TOL
+    a = L.pinned_empty((1000, 451), np.float32)
+    addr = a.ctypes.data
+    a[:] = 1.0
+    del a
+    import gc
+
+    gc.collect()
+    b = L.pinned_empty((1000, 451), np.float32)  # same size class: the pool hands the block back
+    assert b.ctypes.data == addr
