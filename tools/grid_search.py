@@ -1,0 +1,84 @@
+"""BASELINE config 3: fused chi^2 of a mock observation over a ~1e8-point Cartesian parameter grid, generated on
+the device shard by shard (never materialised on the host), rows sharded across the ranks of one node, global
+argmin through torch.distributed (NCCL).
+
+    python tools/grid_search.py [points_per_dim=14] [precision=bf16x3]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/grid_search.py 14
+"""
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from oracle import refmath as rm  # noqa: E402  (prior box + synthetic weights only)
+
+npd = int(sys.argv[1]) if len(sys.argv) > 1 else 14
+prec = sys.argv[2] if len(sys.argv) > 2 else "bf16x3"
+rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+emu_mod = importlib.import_module("21cmvae_b200.emulator")
+pp = importlib.import_module("21cmvae_b200.preprocess")
+kh = importlib.import_module("21cmvae_b200.keras_h5")
+mg = importlib.import_module("21cmvae_b200.multigpu")
+L = importlib.import_module("21cmvae_b200._lib")
+ks, bs, relu = rm.glorot_chain(rm.DIRECT_DIMS, seed=2022)
+mu, sd = rm.synthetic_signal_stats(ks, bs, relu)
+pmin, pmax = rm.prior_par_stats()
+emu = emu_mod.DirectEmulator(stats=pp.NormStats(pmin, pmax, mu, sd), device=local)
+emu.emulator = emu_mod.DenseModel(kh.DenseChainWeights(ks, bs, relu, name="emulator"), device=local)
+h = emu._handle()
+
+# mock observation: the emulator at the notebook's example parameters + 25 mK noise
+truth_p = np.array([0.0003, 4.2, 1e-3, 0.055, 1.0, 0.1, 10.0])
+obs = (rm.predict(truth_p, ks, bs, relu, pmin, pmax, mu, sd) + np.random.default_rng(7).normal(size=451) * 25).astype(np.float32)
+isig = np.full(451, 1 / 25.0, np.float32)
+
+# grid axes in the transformed (log10 for the first three) prior box
+axes = [torch.linspace(float(pmin[j]), float(pmax[j]), npd, dtype=torch.float64, device="cuda") for j in range(7)]
+total = npd**7
+lo, hi = mg.shard_bounds(total, world, rank)
+chunk = 8_000_000
+
+
+def rows_to_params(first, count):
+    idx = torch.arange(first, first + count, device="cuda", dtype=torch.int64)
+    cols = []
+    for j in range(6, -1, -1):
+        cols.append(axes[j][idx % npd])
+        idx = idx // npd
+    p = torch.stack(cols[::-1], dim=1)
+    p[:, :3] = torch.pow(10.0, p[:, :3])
+    return p.contiguous()
+
+
+torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+t0 = time.perf_counter()
+best_v, best_i = float("inf"), -1
+for first in range(lo, hi, chunk):
+    n = min(chunk, hi - first)
+    p = rows_to_params(first, n)
+    _, v, i = h.chi2(p, obs, isig, want_chi2=False, want_best=True, precision=L.PRECISIONS[prec])
+    if i >= 0 and v < best_v:
+        best_v, best_i = v, first - lo + i
+gv, gi = mg.global_argmin(best_v, best_i, lo)
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+if rank == 0:
+    print(json.dumps({"grid_points": total, "points_per_dim": npd, "n_gpus": world, "precision": prec, "seconds": dt,
+                      "points_per_s": total / dt, "chi2_min": gv, "argmin_row": gi,
+                      "argmin_params": rows_to_params(gi, 1)[0].tolist(), "truth_params": truth_p.tolist()}))
+if world > 1:
+    dist.destroy_process_group()
