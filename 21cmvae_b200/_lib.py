@@ -19,9 +19,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VAE21_LIB", os.path.join(_HERE, "libvae21.so"))
 
 F32, F64 = 0, 1
-FP32_SIMT, TC_BF16X3, TC_FP16X3 = 0, 1, 2
+FP32_SIMT, TC_BF16X3, TC_FP16X3, TC_FP16E4M3 = 0, 1, 2, 3
 PRECISIONS = {"fp32": FP32_SIMT, "fp32_simt": FP32_SIMT, "tc": TC_BF16X3, "bf16x3": TC_BF16X3,
-              "tc_bf16x3": TC_BF16X3, "fp16x3": TC_FP16X3, "tc_fp16x3": TC_FP16X3}
+              "tc_bf16x3": TC_BF16X3, "fp16x3": TC_FP16X3, "tc_fp16x3": TC_FP16X3,
+              "fp16e4m3": TC_FP16E4M3, "tc_fp16e4m3": TC_FP16E4M3}
 
 EXPORTS = [
     "vae21_version", "vae21_last_error", "vae21_device_count", "vae21_create", "vae21_destroy",

@@ -24,9 +24,11 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 #include <algorithm>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -73,6 +75,7 @@ struct Layer {
     int out_dst;   // DST_*
     int bias_off;  // float offset into the bias image / smem copy
     int first_chunk, nchunks;
+    float inv_s8;  // FMT 2 only: 1 / S_l, the power-of-two scale the packed weights (hence the accumulators) carry
 };
 
 struct Chunk {
@@ -127,11 +130,17 @@ inline float h162f(unsigned short u) {
     std::memcpy(&h, &u, 2);
     return __half2float(h);
 }
+inline unsigned char f2e4m3(float x) { return static_cast<unsigned char>(__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3)); }
+// FMT 2 ("fp16e4m3"): a*w ~= a_hi*w_hi [kind::f16] + e4m3(a)*e4m3(w_lo*2^11)*2^-11 + e4m3(a_lo*2^11)*2^-11*e4m3(w)  [one kind::f8f6f4
+// MMA, K = 32 = the 16 features' {hi8 | lo8} against {w_lo8 ; w_hi8}].  The 2^-11 cannot be carried by an e4m3 operand (range),
+// so the WHOLE accumulator is kept at scale S_l: w_hi is packed as fp16(w S_l), w_lo8 = e4m3(w S_l - w_hi), w_hi8 = e4m3(w S_l / 2^11)
+// and the epilogue multiplies by 1 / S_l.  S_l = 2^11 unless a layer's weights are large (w S_l must stay inside fp16).
+constexpr float A_LO_SCALE = 2048.f;
 
 // Build the schedule for a Dense stack.  Returns false (with `why`) when the stack does not fit.
 inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, const float* const* kernels,
                             const float* const* biases, const int* relu, Plan& P,
-                            std::vector<unsigned short>* img /*[2]: bf16, fp16*/, std::vector<float>& bias_img,
+                            std::vector<unsigned short>* img /*[3]: bf16, fp16, fp16+e4m3*/, std::vector<float>& bias_img,
                             std::string& why) {
     P = Plan{};
     if (n_layers < 2 || n_layers > MAXL) { why = "needs 2.." + std::to_string(MAXL) + " layers"; return false; }
@@ -299,7 +308,15 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
     // Image 1 (bytes [0, w_bytes)): whole tiles for the one-CTA kernel.
     // Image 2 (bytes [w_bytes, 2 w_bytes)): for the CTA-pair kernel, rank r's half (rows [r n/2, (r+1) n/2) of
     // every tile) at w_bytes + r * w_bytes / 2, same order.
-    for (int f = 0; f < 2; ++f) img[f].assign(P.w_bytes, 0);
+    for (int f = 0; f < 3; ++f) img[f].assign(P.w_bytes, 0);
+    unsigned char* img8 = reinterpret_cast<unsigned char*>(img[2].data());
+    for (int l = 0; l < n_layers; ++l) {
+        float wmax = 0.f;
+        for (size_t i = 0; i < static_cast<size_t>(dims[l]) * dims[l + 1]; ++i) wmax = std::max(wmax, std::fabs(kernels[l][i]));
+        float S = A_LO_SCALE;
+        while (S > 1.f && wmax * S > 32768.f) S *= 0.5f;
+        P.L[l].inv_s8 = 1.f / S;
+    }
     const size_t img2 = P.w_bytes / 2;  // element offset of image 2
     for (int c = 0; c < nchunks; ++c) {
         const Chunk& C = P.C[c];
@@ -330,6 +347,16 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
                     img[1][lo_base + e] = lh;
                     img[1][base2 + e2] = hh;
                     img[1][lo2 + e2] = lh;
+                    // fp16 + e4m3: 16-bit tile = fp16(w S); 8-bit tile = k-group 0: e4m3(w S - hi)[16 k], k-group 1: e4m3(w S / 2^11)[16 k]
+                    const float S = 1.f / P.L[l].inv_s8, ws = w * S;
+                    const unsigned short h8 = f2h16(ws);
+                    const unsigned char wl8 = f2e4m3(ws - h162f(h8)), wh8 = f2e4m3(ws / A_LO_SCALE);
+                    img[2][base + e] = h8;
+                    img[2][base2 + e2] = h8;
+                    img8[2 * lo_base + static_cast<size_t>(nn) * 16 + kk] = wl8;
+                    img8[2 * lo_base + (static_cast<size_t>(C.ncols) + nn) * 16 + kk] = wh8;
+                    img8[2 * lo2 + static_cast<size_t>(nl) * 16 + kk] = wl8;
+                    img8[2 * lo2 + (static_cast<size_t>(hn) + nl) * 16 + kk] = wh8;
                 }
             }
         }
@@ -351,14 +378,13 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
     if (build_plan_with(false, n_layers, dims, kernels, biases, relu, P, img, bias_img, why_a) && P.nslots >= 3) return true;
     Plan Pa = P;
     const bool ok_a = why_a.empty() && Pa.n_chunks > 0 && Pa.nslots >= 2;
-    std::vector<unsigned short> img_b[2];
+    std::vector<unsigned short> img_b[3];
     std::vector<float> bias_b;
     Plan Pb;
     const bool ok_b = build_plan_with(true, n_layers, dims, kernels, biases, relu, Pb, img_b, bias_b, why_b);
     if (ok_b && (!ok_a || Pb.nslots > Pa.nslots)) {
         P = Pb;
-        img[0].swap(img_b[0]);
-        img[1].swap(img_b[1]);
+        for (int f = 0; f < 3; ++f) img[f].swap(img_b[f]);
         bias_img.swap(bias_b);
         return true;
     }
@@ -467,6 +493,39 @@ __device__ __forceinline__ void mma_ts2(uint32_t d, uint32_t ta, uint32_t b_lo, 
         "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
         "mov.b64 db, {%2, %3};\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(d),
+        "r"(ta), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// kind::f8f6f4 (e4m3 x e4m3, K = 32) forms of the four wrappers above / below
+__device__ __forceinline__ void mma8_ss2(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %4, p;\n\t}\n" ::"r"(d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma8_ts2(uint32_t d, uint32_t ta, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(d),
+        "r"(ta), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma8x2_ss2(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], da, db, %4, p;\n\t}\n" ::"r"(d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma8x2_ts2(uint32_t d, uint32_t ta, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(d),
         "r"(ta), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
         : "memory");
 }
@@ -581,6 +640,37 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     }
 }
 
+// Four fp32 values -> the operand words of one k-quad.  FMT 0/1: two hi words + two lo words (16-bit pairs).
+// FMT 2: two fp16 hi words, ONE word of four e4m3(v) and ONE word of four e4m3((v - hi) * 2^11).
+template <int FMT>
+__device__ __forceinline__ void split4_f8(float v0, float v1, float v2, float v3, uint32_t& h01, uint32_t& h23, uint32_t& b_hi8,
+                                          uint32_t& b_lo8) {
+    const __half2 ha = __floats2half2_rn(v0, v1), hb = __floats2half2_rn(v2, v3);
+    h01 = *reinterpret_cast<const uint32_t*>(&ha);
+    h23 = *reinterpret_cast<const uint32_t*>(&hb);
+    const float2 fa = __half22float2(ha), fb = __half22float2(hb);
+    const uint32_t p0 = __nv_cvt_float2_to_fp8x2(make_float2(v0, v1), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t p1 = __nv_cvt_float2_to_fp8x2(make_float2(v2, v3), __NV_SATFINITE, __NV_E4M3);
+    b_hi8 = p0 | (p1 << 16);
+    const uint32_t q0 = __nv_cvt_float2_to_fp8x2(make_float2((v0 - fa.x) * A_LO_SCALE, (v1 - fa.y) * A_LO_SCALE), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t q1 = __nv_cvt_float2_to_fp8x2(make_float2((v2 - fb.x) * A_LO_SCALE, (v3 - fb.y) * A_LO_SCALE), __NV_SATFINITE, __NV_E4M3);
+    b_lo8 = q0 | (q1 << 16);
+}
+// 16 consecutive features of one row -> the 16 operand words of a k-step: w[0..7] = 16-bit hi pairs (k-groups 0 and 1),
+// w[8..15] = second tile (FMT 0/1: lo pairs; FMT 2: w[8..11] e4m3(v) for the 16 k, w[12..15] e4m3 of the scaled remainders).
+template <int FMT>
+__device__ __forceinline__ void split16(const float (&v)[16], uint32_t (&w)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (FMT == 2) {
+            split4_f8<FMT>(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3], w[2 * q], w[2 * q + 1], w[8 + q], w[12 + q]);
+        } else {
+            split2<FMT>(v[4 * q], v[4 * q + 1], w[2 * q], w[8 + 2 * q]);
+            split2<FMT>(v[4 * q + 2], v[4 * q + 3], w[2 * q + 1], w[8 + 2 * q + 1]);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------
@@ -588,7 +678,7 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 // super-tile with cta_group::2 MMAs (M = 256): rank 0 issues every MMA for both CTAs, each CTA streams
 // HALF of every weight tile into its own shared memory and runs its own epilogue on its own 128 rows.
 // The MMA-issuing warp -- the limiter of the one-CTA kernel -- then serves twice the rows per instruction.
-template <int FMT, int CG>  // FMT 0: bf16 split, 1: fp16 split
+template <int FMT, int CG>  // FMT 0: bf16 split (3 MMAs per k-step), 1: fp16 split (3), 2: fp16 + e4m3 corrections (2)
 __global__ void __launch_bounds__(NTHREADS, 1)
 vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormConsts nc, const __grid_constant__ LaunchArgs a,
                 const uint8_t* __restrict__ wimg, const float* __restrict__ bias_g) {
@@ -870,7 +960,29 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                                     const uint32_t bj = (j < KPS ? bs0 : bs1) + static_cast<uint32_t>(j % KPS) * kstep16;
                                     const uint32_t acc0 = (s + j) > 0 ? 1u : 0u;
                                     if (!(DBG & 1)) {
-                                        if (ts) {
+                                        if (FMT == 2) {
+                                            // one kind::f16 MMA (hi x hi) + one kind::f8f6f4 MMA (both correction terms, K = 32)
+                                            if (ts) {
+                                                const uint32_t taj = ta + 16u * j;
+                                                if (PAIR) {
+                                                    mma2_ts2(d, taj, bj, desc_hi, idesc, acc0);
+                                                    mma8x2_ts2(d, taj + 8u, bj + b_lo16, desc_hi, idesc, 1u);
+                                                } else {
+                                                    mma_ts2(d, taj, bj, desc_hi, idesc, acc0);
+                                                    mma8_ts2(d, taj + 8u, bj + b_lo16, desc_hi, idesc, 1u);
+                                                }
+                                            } else {
+                                                const uint32_t aj = a_lo32 + static_cast<uint32_t>(j) * (KSTEP_BYTES >> 4);
+                                                const uint32_t aj_lo = aj + ((2u * A_KG_BYTES) >> 4);
+                                                if (PAIR) {
+                                                    mma2_ss2(d, aj, bj, desc_hi, idesc, acc0);
+                                                    mma8x2_ss2(d, aj_lo, bj + b_lo16, desc_hi, idesc, 1u);
+                                                } else {
+                                                    mma_ss2(d, aj, bj, desc_hi, idesc, acc0);
+                                                    mma8_ss2(d, aj_lo, bj + b_lo16, desc_hi, idesc, 1u);
+                                                }
+                                            }
+                                        } else if (ts) {
                                             const uint32_t taj = ta + 16u * j;
                                             if (PAIR) {
                                                 mma2_ts2(d, taj, bj, desc_hi, idesc, acc0);
@@ -996,14 +1108,13 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                     }
                 }
             }
-            uint32_t hi[8], lo[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) split2<FMT>(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
+            uint32_t w[16];
+            split16<FMT>(x, w);
             uint8_t* a0 = sm + P.off_a0;
-            *reinterpret_cast<uint4*>(a0 + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(a0 + A_KG_BYTES + row * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-            *reinterpret_cast<uint4*>(a0 + 2 * A_KG_BYTES + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            *reinterpret_cast<uint4*>(a0 + 3 * A_KG_BYTES + row * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            *reinterpret_cast<uint4*>(a0 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(a0 + A_KG_BYTES + row * 16) = make_uint4(w[4], w[5], w[6], w[7]);
+            *reinterpret_cast<uint4*>(a0 + 2 * A_KG_BYTES + row * 16) = make_uint4(w[8], w[9], w[10], w[11]);
+            *reinterpret_cast<uint4*>(a0 + 3 * A_KG_BYTES + row * 16) = make_uint4(w[12], w[13], w[14], w[15]);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_a0_ready);
@@ -1031,26 +1142,34 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 const uint32_t tbase = tm + tlane + static_cast<uint32_t>(C.dcol);
                 const int out_dst = L.out_dst;
                 const bool do_relu = L.relu != 0;
+                const float inv_s8 = (FMT == 2) ? L.inv_s8 : 1.f;
                 auto process = [&](uint32_t (&r)[16], int g) {
                     const uint32_t taddr = tbase + static_cast<uint32_t>(16 * g);
                     if (out_dst != DST_FINAL) {
-                        uint32_t w[16];  // [0..7] hi words, [8..15] lo words
+                        uint32_t w[16];  // [0..7] hi words, [8..15] second-tile words (see split16)
+                        float v[16];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float4 b4 = *reinterpret_cast<const float4*>(bl + 16 * g + 4 * q);
-                            float v0 = __uint_as_float(r[4 * q + 0]) + b4.x;
-                            float v1 = __uint_as_float(r[4 * q + 1]) + b4.y;
-                            float v2 = __uint_as_float(r[4 * q + 2]) + b4.z;
-                            float v3 = __uint_as_float(r[4 * q + 3]) + b4.w;
-                            if (do_relu) {
-                                v0 = relu_nan(v0);
-                                v1 = relu_nan(v1);
-                                v2 = relu_nan(v2);
-                                v3 = relu_nan(v3);
+                            if (FMT == 2) {  // accumulators carry the weight scale S_l
+                                v[4 * q + 0] = fmaf(__uint_as_float(r[4 * q + 0]), inv_s8, b4.x);
+                                v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), inv_s8, b4.y);
+                                v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), inv_s8, b4.z);
+                                v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), inv_s8, b4.w);
+                            } else {
+                                v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x;
+                                v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
+                                v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
+                                v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
                             }
-                            split2<FMT>(v0, v1, w[2 * q], w[8 + 2 * q]);
-                            split2<FMT>(v2, v3, w[2 * q + 1], w[8 + 2 * q + 1]);
+                            if (do_relu) {
+                                v[4 * q + 0] = relu_nan(v[4 * q + 0]);
+                                v[4 * q + 1] = relu_nan(v[4 * q + 1]);
+                                v[4 * q + 2] = relu_nan(v[4 * q + 2]);
+                                v[4 * q + 3] = relu_nan(v[4 * q + 3]);
+                            }
                         }
+                        split16<FMT>(v, w);
                         if (out_dst == DST_TMEM) {
                             tmem_st16(taddr, w);  // in place: these 16 columns become the next layer's k-step
                         } else {
@@ -1062,7 +1181,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                         }
                     } else {
                         const int n = C.n0 + 16 * g;
-                        const float s1 = (a.out_mode == OUT_NORMALISED) ? 1.f : nc.sd;
+                        const float s1 = ((a.out_mode == OUT_NORMALISED) ? 1.f : nc.sd) * inv_s8;
                         float v[16];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -1192,6 +1311,8 @@ inline cudaError_t prepare() {
     if ((e = cudaFuncSetAttribute(vae21_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(vae21_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(vae21_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(vae21_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(vae21_tc_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(vae21_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
 }
 
@@ -1205,11 +1326,13 @@ inline cudaError_t launch(const Plan& P, const NormConsts& nc, const LaunchArgs&
     if (cg == 2) {
         const long long nunits = (a.n + 2 * MT - 1) / (2 * MT);
         const int grid = 2 * static_cast<int>(std::min<long long>(nunits, sm_count / 2));
-        return fmt == 0 ? launch_one<0, 2>(P, nc, a, w, bias, grid, st) : launch_one<1, 2>(P, nc, a, w, bias, grid, st);
+        return fmt == 0 ? launch_one<0, 2>(P, nc, a, w, bias, grid, st)
+               : fmt == 1 ? launch_one<1, 2>(P, nc, a, w, bias, grid, st) : launch_one<2, 2>(P, nc, a, w, bias, grid, st);
     }
     const long long ntiles = (a.n + MT - 1) / MT;
     const int grid = static_cast<int>(std::min<long long>(ntiles, sm_count));
-    return fmt == 0 ? launch_one<0, 1>(P, nc, a, w, bias, grid, st) : launch_one<1, 1>(P, nc, a, w, bias, grid, st);
+    return fmt == 0 ? launch_one<0, 1>(P, nc, a, w, bias, grid, st)
+           : fmt == 1 ? launch_one<1, 1>(P, nc, a, w, bias, grid, st) : launch_one<2, 1>(P, nc, a, w, bias, grid, st);
 }
 
 #if VAE21_TC_TIMING

@@ -112,7 +112,7 @@ struct vae21_handle {
     tck::Plan tc{};
     bool tc_ok = false;
     std::string tc_why;
-    void* d_wtc[2] = {nullptr, nullptr};  // packed hi/lo operand images: [0] bf16, [1] fp16
+    void* d_wtc[3] = {nullptr, nullptr, nullptr};  // packed operand images: [0] bf16 hi/lo, [1] fp16 hi/lo, [2] fp16 + e4m3
     float* d_btc = nullptr;
     // constants
     NormConsts nc{};
@@ -233,10 +233,10 @@ int launch_fp32(vae21_handle* h, const LaunchArgs& a, cudaStream_t st) {
 
 int launch(vae21_handle* h, const LaunchArgs& a, int precision, cudaStream_t st) {
     if (precision == VAE21_FP32_SIMT) return launch_fp32(h, a, st);
-    if (precision == VAE21_TC_BF16X3 || precision == VAE21_TC_FP16X3) {
+    if (precision == VAE21_TC_BF16X3 || precision == VAE21_TC_FP16X3 || precision == VAE21_TC_FP16E4M3) {
         if (!h->tc_ok)
             return fail(VAE21_ERR_UNSUPPORTED, "tensor-core path unavailable for this layer stack: %s", h->tc_why.c_str());
-        const int fmt = precision == VAE21_TC_FP16X3 ? 1 : 0;
+        const int fmt = precision == VAE21_TC_FP16X3 ? 1 : precision == VAE21_TC_FP16E4M3 ? 2 : 0;
         cudaError_t e = tck::launch(h->tc, h->nc, a, h->d_wtc[fmt], h->d_btc, fmt, h->sm_count, st);
         if (e != cudaSuccess) return fail(VAE21_ERR_CUDA, "tensor-core kernel launch failed: %s", cudaGetErrorString(e));
         h->launches++;
@@ -402,7 +402,7 @@ int vae21_destroy(vae21_handle* h) {
     }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    void* ptrs[] = {h->d_w32, h->d_b32, h->d_wtc[0], h->d_wtc[1], h->d_btc, h->d_mu, h->d_obs, h->d_isig, h->d_key};
+    void* ptrs[] = {h->d_w32, h->d_b32, h->d_wtc[0], h->d_wtc[1], h->d_wtc[2], h->d_btc, h->d_mu, h->d_obs, h->d_isig, h->d_key};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete h;
@@ -429,10 +429,10 @@ int vae21_set_model(vae21_handle* h, int n_layers, const int* dims, const float*
     h->tc_ok = false;
     {
         std::string why;
-        std::vector<unsigned short> img[2];
+        std::vector<unsigned short> img[3];
         std::vector<float> bias_img;
         if (tck::build_plan(n_layers, dims, kernels, biases, relu_flags, h->tc, img, bias_img, why)) {
-            for (int f = 0; f < 2; ++f) {
+            for (int f = 0; f < 3; ++f) {
                 if (h->d_wtc[f]) cudaFree(h->d_wtc[f]);
                 h->d_wtc[f] = nullptr;
                 CK(cudaMalloc(&h->d_wtc[f], img[f].size() * sizeof(unsigned short)));

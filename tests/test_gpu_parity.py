@@ -58,7 +58,7 @@ def test_fp32_config1_matches_oracle(rm, direct_fixture, emu_direct):
     assert _rel_err(got, want32.astype(np.float64)) <= FP32_TOL
 
 
-@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3"])
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3", "fp16e4m3"])
 def test_tc_config1_within_mk_tolerance(rm, direct_fixture, emu_direct, prec):
     tc_or_skip(emu_direct)
     params = rm.draw_params(1024, seed=1024)
@@ -96,11 +96,12 @@ def test_fp32_ragged_sizes(rm, direct_fixture, emu_direct, n):
         assert _rel_err(got, want) <= FP32_TOL
 
 
+@pytest.mark.parametrize("prec", [1, 3])
 @pytest.mark.parametrize("n", [1, 127, 129, 1000])
-def test_tc_ragged_sizes(rm, direct_fixture, emu_direct, n):
+def test_tc_ragged_sizes(rm, direct_fixture, emu_direct, n, prec):
     tc_or_skip(emu_direct)
     params = rm.draw_params(n, seed=200 + n, zero_fx_frac=0.2)
-    got = emu_direct._handle().predict(params, precision=1).astype(np.float64)
+    got = emu_direct._handle().predict(params, precision=prec).astype(np.float64)
     d = got - _oracle(rm, direct_fixture, params, squeeze=False)
     assert np.sqrt(np.mean(d * d, axis=1)).max() <= TC_RMS_TOL_MK and np.abs(d).max() <= TC_MAX_TOL_MK
 
@@ -144,14 +145,15 @@ def test_ae_chain_forward_matches_float64_kats(ae_golden):
     assert abs(float(y[0].astype(np.float64).sum()) - 9.912912209957) < 2e-3 and int(y[0].argmin()) == 89
 
 
-def test_ae_chain_tc_if_supported(ae_golden):
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16e4m3"])
+def test_ae_chain_tc_if_supported(ae_golden, prec):
     emu = pkg("emulator")
     kh = pkg("keras_h5")
     g = ae_golden
     m = emu.DenseModel(kh.DenseChainWeights(g["kernels"], g["biases"], g["relu"], name="ae_chain"))
     if not m.handle.info()["tc_supported"]:
         pytest.skip("AE chain does not fit the tensor-core plan")
-    y = m.predict(g["x"], precision="bf16x3").astype(np.float64)
+    y = m.predict(g["x"], precision=prec).astype(np.float64)
     # sigma units; 50 mK per sigma => 0.01 mK rms = 2e-4 sigma, 0.05 mK max = 1e-3 sigma
     d = y - g["y64"]
     assert np.sqrt(np.mean(d * d, axis=1)).max() <= 2e-4 and np.abs(d).max() <= 1e-3

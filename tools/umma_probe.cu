@@ -557,6 +557,317 @@ static int run_cluster() {
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// kind::f8f6f4 (e4m3 x e4m3, K = 32 per instruction) probe: validates the un-swizzled K-major operand image for
+// 8-bit elements ([k/16][row][16 x 8 bit]), A from TMEM (four elements per 32-bit column, byte 0 = lowest k) and
+// -- with mixed = 1 -- accumulating kind::f16 and kind::f8f6f4 MMAs into the SAME fp32 accumulator.
+//   umma_probe f <N> <K> <a_tmem> <mixed>
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+probe_f8_kernel(const uint8_t* __restrict__ A8, const uint8_t* __restrict__ B8img, const uint16_t* __restrict__ A16,
+                const uint16_t* __restrict__ B16img, float* __restrict__ D, int N, int K, int a_tmem, int mixed, int* flag) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA8 = smem;                                           // [K/16][128][16]
+    uint8_t* sB8 = sA8 + 128 * K;                                  // [K/16][N][16]
+    uint16_t* sA16 = reinterpret_cast<uint16_t*>(sB8 + N * K);     // [K/8][128][8]
+    uint16_t* sB16 = sA16 + 128 * K;                               // [K/8][N][8]
+    __shared__ __align__(8) uint64_t bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < 128 * K; e += 128) {
+        const int m = e / K, k = e - m * K;
+        sA8[((k >> 4) * 128 + m) * 16 + (k & 15)] = A8[e];
+        sA16[((k >> 3) * 128 + m) * 8 + (k & 7)] = A16[e];
+    }
+    for (int e = tid; e < N * K; e += 128) {
+        sB8[e] = B8img[e];
+        sB16[e] = B16img[e];
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_mma)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tm = tmem_base_s;
+    const uint32_t tmemA8 = 256, tmemA16 = 256 + 64;  // K <= 256: 64 columns of 8-bit, then K/2 columns of 16-bit
+    if (a_tmem) {
+        for (int c = 0; c < K / 4; c += 8) {
+            uint32_t r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = 4 * (c + i);
+                r[i] = (uint32_t)A8[tid * K + k] | ((uint32_t)A8[tid * K + k + 1] << 8) | ((uint32_t)A8[tid * K + k + 2] << 16) |
+                       ((uint32_t)A8[tid * K + k + 3] << 24);
+            }
+            const uint32_t addr = tm + ((uint32_t)(warp * 32) << 16) + tmemA8 + c;
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(addr), "r"(r[0]),
+                         "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+        }
+        for (int c = 0; c < K / 2; c += 8) {
+            uint32_t r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = 2 * (c + i);
+                r[i] = (uint32_t)A16[tid * K + k] | ((uint32_t)A16[tid * K + k + 1] << 16);
+            }
+            const uint32_t addr = tm + ((uint32_t)(warp * 32) << 16) + tmemA16 + c;
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(addr), "r"(r[0]),
+                         "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+    }
+    if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t idesc8 = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // e4m3 x e4m3 -> f32
+        const uint32_t idesc16 = idesc8;                                                               // f16 x f16 -> f32
+        uint32_t acc = 0;
+        if (mixed) {  // 16-bit pass first, the 8-bit MMAs then accumulate on top
+            for (int ks = 0; ks < K / 16; ++ks) {
+                const uint64_t db = make_desc(smem_u32(sB16) + ks * 2 * N * 16, (uint32_t)N * 16, 128);
+                if (a_tmem) {
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tm),
+                                 "r"(tm + tmemA16 + ks * 8), "l"(db), "r"(idesc16), "r"(acc) : "memory");
+                } else {
+                    const uint64_t da = make_desc(smem_u32(sA16) + ks * 2 * 2048, 2048, 128);
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tm),
+                                 "l"(da), "l"(db), "r"(idesc16), "r"(acc) : "memory");
+                }
+                acc = 1;
+            }
+        }
+        for (int ks = 0; ks < K / 32; ++ks) {
+            const uint64_t db = make_desc(smem_u32(sB8) + ks * 2 * N * 16, (uint32_t)N * 16, 128);
+            if (a_tmem) {
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tm),
+                             "r"(tm + tmemA8 + ks * 8), "l"(db), "r"(idesc8), "r"(acc) : "memory");
+            } else {
+                const uint64_t da = make_desc(smem_u32(sA8) + ks * 2 * 2048, 2048, 128);
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tm),
+                             "l"(da), "l"(db), "r"(idesc8), "r"(acc) : "memory");
+            }
+            acc = 1;
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar_mma)) : "memory");
+    }
+    if (!mbar_wait(&bar_mma, 0, flag, 12)) return;
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    for (int c = 0; c < N; c += 8) {
+        uint32_t r[8];
+        const uint32_t addr = tm + ((uint32_t)(warp * 32) << 16) + c;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(addr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 8; ++i) D[tid * N + c + i] = __uint_as_float(r[i]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512));
+}
+
+// e4m3 encoding of a multiple of 1/8 in [-1, 1] (exact): sign | exponent (bias 7) | 3 mantissa bits
+static uint8_t to_e4m3_exact(float x) {
+    if (x == 0.f) return 0;
+    const uint8_t sgn = x < 0 ? 0x80 : 0;
+    float a = fabsf(x);
+    int e = 0;
+    while (a < 1.f) { a *= 2.f; --e; }
+    while (a >= 2.f) { a *= 0.5f; ++e; }
+    const int mant = (int)((a - 1.f) * 8.f + 0.5f);
+    return sgn | (uint8_t)((e + 7) << 3) | (uint8_t)mant;
+}
+static uint16_t to16(float x, int fp16);
+static int run_f8(int argc, char** argv) {
+    const int N = argc > 2 ? atoi(argv[2]) : 64, K = argc > 3 ? atoi(argv[3]) : 32, a_tmem = argc > 4 ? atoi(argv[4]) : 0,
+              mixed = argc > 5 ? atoi(argv[5]) : 0;
+    std::vector<float> A8f(128 * K), B8f(N * K), A16f(128 * K), B16f(N * K);
+    uint32_t s = 777u + N + K;
+    auto rnd = [&]() {
+        s = s * 1664525u + 1013904223u;
+        return (float)((int)((s >> 16) % 17) - 8) / 8.0f;
+    };
+    for (auto& x : A8f) x = rnd();
+    for (auto& x : B8f) x = rnd();
+    for (auto& x : A16f) x = rnd();
+    for (auto& x : B16f) x = rnd();
+    std::vector<uint8_t> A8(128 * K), B8(N * K);
+    std::vector<uint16_t> A16(128 * K), B16(N * K);
+    for (int i = 0; i < 128 * K; ++i) { A8[i] = to_e4m3_exact(A8f[i]); A16[i] = to16(A16f[i], 1); }
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) {
+            B8[((k >> 4) * N + n) * 16 + (k & 15)] = to_e4m3_exact(B8f[n * K + k]);
+            B16[((k >> 3) * N + n) * 8 + (k & 7)] = to16(B16f[n * K + k], 1);
+        }
+    std::vector<float> ref(128 * N);
+    for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < N; ++n) {
+            float acc = 0;
+            for (int k = 0; k < K; ++k) acc += A8f[m * K + k] * B8f[n * K + k] + (mixed ? A16f[m * K + k] * B16f[n * K + k] : 0.f);
+            ref[m * N + n] = acc;
+        }
+    uint8_t *dA8, *dB8;
+    uint16_t *dA16, *dB16;
+    float* dD;
+    int* dflag;
+    CK(cudaMalloc(&dA8, A8.size())); CK(cudaMalloc(&dB8, B8.size()));
+    CK(cudaMalloc(&dA16, A16.size() * 2)); CK(cudaMalloc(&dB16, B16.size() * 2));
+    CK(cudaMalloc(&dD, ref.size() * 4)); CK(cudaMalloc(&dflag, 4));
+    CK(cudaMemset(dflag, 0, 4)); CK(cudaMemset(dD, 0xff, ref.size() * 4));
+    CK(cudaMemcpy(dA8, A8.data(), A8.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB8, B8.data(), B8.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dA16, A16.data(), A16.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB16, B16.data(), B16.size() * 2, cudaMemcpyHostToDevice));
+    const size_t smem = (size_t)3 * (128 + N) * K + 1024;
+    CK(cudaFuncSetAttribute(probe_f8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    probe_f8_kernel<<<1, 128, smem>>>(dA8, dB8, dA16, dB16, dD, N, K, a_tmem, mixed, dflag);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    std::vector<float> out(ref.size());
+    int flag = 0;
+    CK(cudaMemcpy(out.data(), dD, out.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&flag, dflag, 4, cudaMemcpyDeviceToHost));
+    int bad = 0;
+    for (size_t i = 0; i < ref.size(); ++i) bad += !(out[i] == ref[i]);
+    printf("f8 probe N=%d K=%d a_tmem=%d mixed=%d : flag=%d mismatches=%d/%zu  %s\n", N, K, a_tmem, mixed, flag, bad, ref.size(),
+           (bad == 0 && flag == 0) ? "PASS" : "FAIL");
+    int shown = 0;
+    for (size_t i = 0; i < ref.size() && shown < 6 && bad; ++i)
+        if (out[i] != ref[i]) { printf("   [m=%zu n=%zu] got %g want %g\n", i / N, i % N, out[i], ref[i]); ++shown; }
+    return (bad == 0 && flag == 0) ? 0 : 3;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Timing v4: cycles per MMA for kind::f16 (K = 16) vs kind::f8f6f4 (K = 32), one CTA or a CTA pair (cta_group::2, M = 256).
+//   umma_probe u
+// ---------------------------------------------------------------------------------------------
+template <int CG, int KIND, int G>
+__global__ void __launch_bounds__(128, 1)
+time_kernel4(int N, int a_tmem, int nmma, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint32_t rank = 0;
+    if (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
+    for (int e = tid; e < 64 * 1024 / 4; e += 128) reinterpret_cast<uint32_t*>(smem)[e] = KIND ? 0x38383838u : 0x3c003c00u;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (CG == 2) asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tm = tmem_base_s;
+    if (warp == 0 && rank == 0) {
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((CG * 128) >> 4) << 24);
+        const uint32_t sA = smem_u32(smem), sB = smem_u32(smem) + 32768;
+        const uint32_t b_kg = (uint32_t)(N / CG) * 16;
+        const uint64_t da = make_desc(sA, 2048, 128);
+        const uint64_t db = make_desc(sB, b_kg, 128);
+        const long long t0 = clock64();
+        for (int i = 0; i < nmma; i += G) {
+            if (elect_one()) {
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    const uint64_t dbi = db + (uint64_t)(((u & 3) * 2 * b_kg) >> 4);
+                    const uint64_t dai = da + (uint64_t)(((u & 3) * 4096) >> 4);
+                    const uint32_t ta = tm + 448u + (u & 3) * 8;
+#define MMA4(cg, kind)                                                                                                                  \
+    if (a_tmem)                                                                                                                          \
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::" cg ".kind::" kind " [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tm), \
+                     "r"(ta), "l"(dbi), "r"(idesc), "r"(1u) : "memory");                                                               \
+    else                                                                                                                                 \
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::" cg ".kind::" kind " [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tm),   \
+                     "l"(dai), "l"(dbi), "r"(idesc), "r"(1u) : "memory");
+                    if (CG == 1 && KIND == 0) { MMA4("1", "f16") }
+                    if (CG == 1 && KIND == 1) { MMA4("1", "f8f6f4") }
+                    if (CG == 2 && KIND == 0) { MMA4("2", "f16") }
+                    if (CG == 2 && KIND == 1) { MMA4("2", "f8f6f4") }
+                }
+            }
+            __syncwarp();
+        }
+        if (elect_one()) {
+            if (CG == 2)
+                asm volatile("{\n\t.reg .b16 m;\n\tmov.b16 m, 1;\n\ttcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}\n" ::"r"(smem_u32(&bar)) : "memory");
+            else
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar)) : "memory");
+        }
+        __syncwarp();
+        mbar_wait(&bar, 0, nullptr, 0);
+        const long long t1 = clock64();
+        if ((tid & 31) == 0) out[0] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (CG == 2) asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    if (warp == 0) {
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512));
+    }
+}
+template <int CG, int KIND>
+static int run4(int N, int a_tmem, long long* d) {
+    const int nmma = 1536;
+    cudaFuncSetAttribute(time_kernel4<CG, KIND, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(CG);
+        cfg.blockDim = dim3(128);
+        cfg.dynamicSmemBytes = 96 * 1024;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CG;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, time_kernel4<CG, KIND, 6>, N, a_tmem, nmma, d));
+        CK(cudaDeviceSynchronize());
+    }
+    long long c = 0;
+    CK(cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost));
+    printf("timing4 cta_group=%d kind=%s N=%d a_tmem=%d : %.1f cycles/MMA (N/2 = %d)\n", CG, KIND ? "f8f6f4(K32)" : "f16(K16)", N, a_tmem,
+           (double)c / nmma, N / 2);
+    return 0;
+}
+static int run_timing4() {
+    long long* d;
+    CK(cudaMalloc(&d, 8));
+    for (int N : {112, 144, 176, 192, 224, 256})
+        for (int at = 0; at < 2; ++at) {
+            run4<1, 0>(N, at, d);
+            run4<1, 1>(N, at, d);
+            run4<2, 0>(N, at, d);
+            run4<2, 1>(N, at, d);
+        }
+    return 0;
+}
+
 static uint16_t to16(float x, int fp16) {
     if (fp16) {
         __half h = __float2half_rn(x);
@@ -591,6 +902,8 @@ int main(int argc, char** argv) {
     }
     if (argv[1][0] == 'c') return run_cluster();
     if (argv[1][0] == 't') return run_timing(argc, argv);
+    if (argv[1][0] == 'f') return run_f8(argc, argv);
+    if (argv[1][0] == 'u') return run_timing4();
     const int vi = atoi(argv[1]);
     if (vi < 0 || vi >= nvar) return 1;
     const Variant v = table[vi];
