@@ -48,7 +48,8 @@ constexpr int MAXL = 8;
 constexpr int MAXC = 32;
 constexpr int NFULL = 4;          // ring of "accumulator chunk ready" barriers
 #ifndef VAE21_TC_ABLATE
-#define VAE21_TC_ABLATE 0  // profiling only: 1 no MMA issue, 2 no epilogue work, 4 no weight copies (bit mask)
+#define VAE21_TC_ABLATE 0  // profiling only (bit mask): 1 no MMA issue, 2 no epilogue work, 4 no weight copies, 8 no final-layer stores,
+                           // 16 no hi/lo split arithmetic, 32 no hidden-layer operand writes, 128 no weight ring at all (MMAs read stale smem)
 #endif
 constexpr int DBG = VAE21_TC_ABLATE;
 #ifndef VAE21_TC_TIMING
@@ -57,7 +58,11 @@ constexpr int DBG = VAE21_TC_ABLATE;
 #if VAE21_TC_TIMING
 __device__ long long g_tc_timing[160][16];  // [cta][0 total, 1..5 operand-ready wait by consuming layer, 6..10 q_empty wait by layer, 11 ring, 12 rendezvous, 13 issue]
 #endif
-constexpr int MAX_SLOTS = 8;
+constexpr int MAX_SLOTS = 16;
+#ifndef VAE21_TC_KPS
+#define VAE21_TC_KPS 2   // k-steps per ring slot of the CTA-pair kernel (1 or 2; 1 measured slower: 2.05 vs 1.90 ms)
+#endif
+constexpr int BAR_BYTES = 512;  // barrier block at off_bar (2 * MAX_SLOTS + NFULL + 2 + MAX_LCHUNK + 1 barriers + the TMEM base word)
 constexpr int MAX_LCHUNK = 4;      // chunks per non-final layer (per-chunk operand-ready barriers)
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int KSTEP_BYTES = 8192; // one k-step (16 features) of a 128-row activation tile: hi 4 KB + lo 4 KB
@@ -84,6 +89,7 @@ struct Chunk {
     int dcol;        // TMEM column of the accumulator
     int qbuf;        // 0/1: ring buffer index, -1: in place (stays in TMEM as next layer's operand)
     int nstages;     // weight stages (each 16 k wide, hi+lo) == K/16
+    int kps2;        // pair kernel: k-steps per ring slot for this chunk (as many as fit the slot, at most 4)
     unsigned w_off;  // byte offset of the first stage in the weight image
 };
 
@@ -201,7 +207,8 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
         const int freec = 512 - lo;
         nbuf = 2;
         qsize = std::min(256, (freec / 2) / 16 * 16);
-        if (qsize < 112) {
+        static const int min_q = std::getenv("VAE21_TC_MINQ") ? std::atoi(std::getenv("VAE21_TC_MINQ")) : 112;
+        if (qsize < min_q) {
             nbuf = 1;
             qsize = std::min(256, freec / 16 * 16);
         }
@@ -285,7 +292,7 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
     P.off_isig = off;
     off += nop * 4;
     P.off_bar = off;
-    off += 256 + 2 * 16 * 4 + 2 * (EPS - 1) * 128 * 4;  // barriers + prologue constants + chi^2 partials
+    off += BAR_BYTES + 2 * 16 * 4 + 2 * (EPS - 1) * 128 * 4;  // barriers + prologue constants + chi^2 partials
     off = (off + 127) / 128 * 128;
     P.off_ring = off;
     const int avail = SMEM_LIMIT - 128 /*alignment slack*/ - off;
@@ -293,8 +300,12 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
     if (P.nslots < 2) { why = "shared memory: activations leave no room for a weight ring"; return false; }
     // pair kernel: each CTA holds half of every B tile, so a slot of the same size holds TWO k-steps: the same bytes
     // in flight with half as many barrier round trips (the ring protocol is latency-, not bandwidth-bound)
-    P.slot_bytes2 = P.slot_bytes;
+    P.slot_bytes2 = P.slot_bytes / 2 * VAE21_TC_KPS;
     P.nslots2 = std::min(MAX_SLOTS, avail / P.slot_bytes2) & ~1;  // even: the MMA loop consumes slots in pairs
+    // narrow chunks would leave most of a slot empty (112 columns: half): pack up to 4 k-steps of this CTA's half tile into a slot
+    static const int kps_max = std::getenv("VAE21_TC_KPS_MAX") ? std::atoi(std::getenv("VAE21_TC_KPS_MAX")) : 4;
+    for (int c = 0; c < nchunks; ++c)
+        P.C[c].kps2 = std::max(VAE21_TC_KPS, std::min(std::max(kps_max, VAE21_TC_KPS), P.slot_bytes2 / (P.C[c].ncols * 32)));
     P.smem_total2 = off + P.nslots2 * P.slot_bytes2 + 128;
     // Two issuing warps alternate loop iterations of two slots each.  mbarrier waits are by phase PARITY, so each
     // issuer must observe every ring cycle at least once: with fewer than 4 slots (one iteration per cycle) an issuer
@@ -689,7 +700,6 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr bool PAIR = (CG == 2);
-    constexpr int KPS = PAIR ? 2 : 1;  // k-steps per ring slot
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = (rank == 0);
     // work units: 128-row tiles (CG 1) or 256-row super-tiles (CG 2); this CTA's tile of unit u is CG*u + rank
@@ -705,7 +715,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     auto bar_act_ready = [&](int j) { return bar0 + 8u * (2 * MAX_SLOTS + NFULL + 2 + j); };  // j < MAX_LCHUNK
     const uint32_t bar_a0_ready = bar0 + 8u * (2 * MAX_SLOTS + NFULL + 2 + MAX_LCHUNK);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + P.off_bar + 8 * (2 * MAX_SLOTS + NFULL + 3 + MAX_LCHUNK));
-    float* s_pmin = reinterpret_cast<float*>(sm + P.off_bar + 256);   // [16] fp32 copies of the prologue constants
+    float* s_pmin = reinterpret_cast<float*>(sm + P.off_bar + BAR_BYTES);   // [16] fp32 copies of the prologue constants
     float* s_pscale = s_pmin + 16;                                    // [16] 2 / (pmax - pmin)
     float* s_chi = s_pscale + 16;                                     // [2][EPS-1][128] chi^2 partials of the other column shares
 
@@ -773,7 +783,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
 
     if (warp == 0) {
         // ===================== producer: stream the weight image through the ring ============
-        if (lane == 0) {
+        if (lane == 0 && !(DBG & 128)) {
             int slot = 0;
             uint32_t phase = 0;
             for (long long unit = unit0; unit < nunits; unit += ustep) {
@@ -783,8 +793,9 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                     const uint8_t* src = PAIR ? wimg + P.w_bytes + static_cast<size_t>(rank) * (P.w_bytes / 2) + C.w_off / 2
                                               : wimg + C.w_off;
                     const int nst = C.nstages;
-                    for (int s = 0; s < nst; s += KPS) {
-                        const uint32_t sbytes = bytes * static_cast<uint32_t>(min(KPS, nst - s));  // k-steps in this slot
+                    const int kps = PAIR ? C.kps2 : 1;
+                    for (int s = 0; s < nst; s += kps) {
+                        const uint32_t sbytes = bytes * static_cast<uint32_t>(min(kps, nst - s));  // k-steps in this slot
                         mbar_wait(bar_ring_empty(slot), phase ^ 1u);
                         if (DBG & 4) {
                             mbar_arrive(bar_ring_full(slot));
@@ -901,12 +912,13 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
 #if VAE21_TC_TIMING
                 tm_setup += clock64() - t_chunk0;
 #endif
-                for (int s = 0, it = 0; s < nst; s += 2 * KPS, ++it) {
+                const int kps = PAIR ? C.kps2 : 1;  // k-steps per ring slot
+                for (int s = 0, it = 0; s < nst; s += 2 * kps, ++it) {
 #if VAE21_TC_TIMING
                     const long long t_it0 = clock64();
 #endif
-                    const int nk = min(2 * KPS, nst - s);  // k-steps of this iteration (two ring slots' worth)
-                    const bool two = (nk > KPS);           // second slot in use
+                    const int nk = min(2 * kps, nst - s);  // k-steps of this iteration (two ring slots' worth)
+                    const bool two = (nk > kps);           // second slot in use
                     // the k-steps of this iteration may cross into the next chunk of the producing layer
                     if (s + nk - 1 >= next_src_k) {
                         do {
@@ -927,6 +939,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                     const bool mine = !two_issuers || ((it & 1) == mw);
                     if (!mine) {
                         // the other issuing warp handles this iteration
+                    } else if ((DBG & 128) && PAIR && !leader) {
                     } else if (PAIR && !leader) {
                         // forwarder: my halves of these stages have landed -> tell the issuer
                         mbar_wait(full0, rphase);
@@ -940,8 +953,8 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                         // probe both stages' barriers back to back (their ~90-cycle latencies overlap)
                         {
                             TSTART
-                            uint32_t ok = mbar_try(full0, rphase);
-                            if (two) ok &= mbar_try(full1, ph1);
+                            uint32_t ok = (DBG & 128) ? 1u : mbar_try(full0, rphase);
+                            if (two && !(DBG & 128)) ok &= mbar_try(full1, ph1);
                             if (!ok) {
                                 mbar_wait(full0, rphase);
                                 if (two) mbar_wait(full1, ph1);
@@ -954,67 +967,66 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
 #endif
                         const uint32_t bs0 = b_base32 + slot * slot16, bs1 = b_base32 + slot1 * slot16;
                         if (elect_one()) {
-#pragma unroll
-                            for (int j = 0; j < 2 * KPS; ++j) {
-                                if (j < nk) {
-                                    const uint32_t bj = (j < KPS ? bs0 : bs1) + static_cast<uint32_t>(j % KPS) * kstep16;
-                                    const uint32_t acc0 = (s + j) > 0 ? 1u : 0u;
-                                    if (!(DBG & 1)) {
-                                        if (FMT == 2) {
-                                            // one kind::f16 MMA (hi x hi) + one kind::f8f6f4 MMA (both correction terms, K = 32)
-                                            if (ts) {
-                                                const uint32_t taj = ta + 16u * j;
-                                                if (PAIR) {
-                                                    mma2_ts2(d, taj, bj, desc_hi, idesc, acc0);
-                                                    mma8x2_ts2(d, taj + 8u, bj + b_lo16, desc_hi, idesc, 1u);
-                                                } else {
-                                                    mma_ts2(d, taj, bj, desc_hi, idesc, acc0);
-                                                    mma8_ts2(d, taj + 8u, bj + b_lo16, desc_hi, idesc, 1u);
-                                                }
-                                            } else {
-                                                const uint32_t aj = a_lo32 + static_cast<uint32_t>(j) * (KSTEP_BYTES >> 4);
-                                                const uint32_t aj_lo = aj + ((2u * A_KG_BYTES) >> 4);
-                                                if (PAIR) {
-                                                    mma2_ss2(d, aj, bj, desc_hi, idesc, acc0);
-                                                    mma8x2_ss2(d, aj_lo, bj + b_lo16, desc_hi, idesc, 1u);
-                                                } else {
-                                                    mma_ss2(d, aj, bj, desc_hi, idesc, acc0);
-                                                    mma8_ss2(d, aj_lo, bj + b_lo16, desc_hi, idesc, 1u);
-                                                }
-                                            }
-                                        } else if (ts) {
-                                            const uint32_t taj = ta + 16u * j;
-                                            if (PAIR) {
-                                                mma2_ts2(d, taj, bj, desc_hi, idesc, acc0);
-                                                mma2_ts2(d, taj, bj + b_lo16, desc_hi, idesc, 1u);
-                                                mma2_ts2(d, taj + 8u, bj, desc_hi, idesc, 1u);
-                                            } else {
-                                                mma_ts2(d, taj, bj, desc_hi, idesc, acc0);
-                                                mma_ts2(d, taj, bj + b_lo16, desc_hi, idesc, 1u);
-                                                mma_ts2(d, taj + 8u, bj, desc_hi, idesc, 1u);
-                                            }
+                            // one k-step: kind::f16 hi x hi plus the correction MMA(s) of the operand format
+                            auto kstep = [&](int j, uint32_t bj) {
+                                const uint32_t acc0 = (s + j) > 0 ? 1u : 0u;
+                                if (DBG & 1) return;
+                                if (ts) {
+                                    const uint32_t taj = ta + 16u * j;
+                                    if (FMT == 2) {
+                                        if (PAIR) {
+                                            mma2_ts2(d, taj, bj, desc_hi, idesc, acc0);
+                                            mma8x2_ts2(d, taj + 8u, bj + b_lo16, desc_hi, idesc, 1u);
                                         } else {
-                                            const uint32_t aj = a_lo32 + static_cast<uint32_t>(j) * (KSTEP_BYTES >> 4);
-                                            const uint32_t aj_lo = aj + ((2u * A_KG_BYTES) >> 4);
-                                            if (PAIR) {
-                                                mma2_ss2(d, aj, bj, desc_hi, idesc, acc0);
-                                                mma2_ss2(d, aj, bj + b_lo16, desc_hi, idesc, 1u);
-                                                mma2_ss2(d, aj_lo, bj, desc_hi, idesc, 1u);
-                                            } else {
-                                                mma_ss2(d, aj, bj, desc_hi, idesc, acc0);
-                                                mma_ss2(d, aj, bj + b_lo16, desc_hi, idesc, 1u);
-                                                mma_ss2(d, aj_lo, bj, desc_hi, idesc, 1u);
-                                            }
+                                            mma_ts2(d, taj, bj, desc_hi, idesc, acc0);
+                                            mma8_ts2(d, taj + 8u, bj + b_lo16, desc_hi, idesc, 1u);
                                         }
+                                    } else if (PAIR) {
+                                        mma2_ts2(d, taj, bj, desc_hi, idesc, acc0);
+                                        mma2_ts2(d, taj, bj + b_lo16, desc_hi, idesc, 1u);
+                                        mma2_ts2(d, taj + 8u, bj, desc_hi, idesc, 1u);
+                                    } else {
+                                        mma_ts2(d, taj, bj, desc_hi, idesc, acc0);
+                                        mma_ts2(d, taj, bj + b_lo16, desc_hi, idesc, 1u);
+                                        mma_ts2(d, taj + 8u, bj, desc_hi, idesc, 1u);
                                     }
-                                    // last k-step of a slot: free it (in both CTAs of a pair) once these MMAs have read it
-                                    if (j == KPS - 1 || (j < KPS && j == nk - 1)) {
-                                        if (PAIR) mma2_commit_both(full0 + 8u * MAX_SLOTS);
-                                        else mma_commit(full0 + 8u * MAX_SLOTS);
-                                    } else if (j >= KPS && j == nk - 1) {
-                                        if (PAIR) mma2_commit_both(full1 + 8u * MAX_SLOTS);
-                                        else mma_commit(full1 + 8u * MAX_SLOTS);
+                                } else {
+                                    const uint32_t aj = a_lo32 + static_cast<uint32_t>(j) * (KSTEP_BYTES >> 4);
+                                    const uint32_t aj_lo = aj + ((2u * A_KG_BYTES) >> 4);
+                                    if (FMT == 2) {
+                                        if (PAIR) {
+                                            mma2_ss2(d, aj, bj, desc_hi, idesc, acc0);
+                                            mma8x2_ss2(d, aj_lo, bj + b_lo16, desc_hi, idesc, 1u);
+                                        } else {
+                                            mma_ss2(d, aj, bj, desc_hi, idesc, acc0);
+                                            mma8_ss2(d, aj_lo, bj + b_lo16, desc_hi, idesc, 1u);
+                                        }
+                                    } else if (PAIR) {
+                                        mma2_ss2(d, aj, bj, desc_hi, idesc, acc0);
+                                        mma2_ss2(d, aj, bj + b_lo16, desc_hi, idesc, 1u);
+                                        mma2_ss2(d, aj_lo, bj, desc_hi, idesc, 1u);
+                                    } else {
+                                        mma_ss2(d, aj, bj, desc_hi, idesc, acc0);
+                                        mma_ss2(d, aj, bj + b_lo16, desc_hi, idesc, 1u);
+                                        mma_ss2(d, aj_lo, bj, desc_hi, idesc, 1u);
                                     }
+                                }
+                            };
+                            // first ring slot of this iteration, then (if in use) the second; each slot is freed -- in both CTAs of a
+                            // pair -- by a commit behind the MMAs of its last k-step
+                            const int n0k = min(nk, kps);
+#pragma unroll 4
+                            for (int j = 0; j < n0k; ++j) kstep(j, bs0 + static_cast<uint32_t>(j) * kstep16);
+                            if (!(DBG & 128)) {
+                                if (PAIR) mma2_commit_both(full0 + 8u * MAX_SLOTS);
+                                else mma_commit(full0 + 8u * MAX_SLOTS);
+                            }
+                            if (two) {
+#pragma unroll 4
+                                for (int j = kps; j < nk; ++j) kstep(j, bs1 + static_cast<uint32_t>(j - kps) * kstep16);
+                                if (!(DBG & 128)) {
+                                    if (PAIR) mma2_commit_both(full1 + 8u * MAX_SLOTS);
+                                    else mma_commit(full1 + 8u * MAX_SLOTS);
                                 }
                             }
                         }
@@ -1031,8 +1043,8 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                         tc_fence_after();
                         TADD(tm_rdv)
                     }
-                    a_lo32 += static_cast<uint32_t>(2 * KPS) * (KSTEP_BYTES >> 4);
-                    ta += 32u * KPS;
+                    a_lo32 += static_cast<uint32_t>(2 * kps) * (KSTEP_BYTES >> 4);
+                    ta += 32u * static_cast<uint32_t>(kps);
                     slot += two ? 2 : 1;
                     if (slot >= nslots) {
                         slot -= nslots;
@@ -1169,8 +1181,15 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                                 v[4 * q + 3] = relu_nan(v[4 * q + 3]);
                             }
                         }
-                        split16<FMT>(v, w);
-                        if (out_dst == DST_TMEM) {
+                        if (DBG & 16) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) w[i] = __float_as_uint(v[i]);
+                        } else {
+                            split16<FMT>(v, w);
+                        }
+                        if (DBG & 32) {
+                            if (w[3] == 0x12345u) tmem_st16(taddr, w);
+                        } else if (out_dst == DST_TMEM) {
                             tmem_st16(taddr, w);  // in place: these 16 columns become the next layer's k-step
                         } else {
                             uint8_t* dst = sm + P.off_act + ((C.n0 >> 4) + g) * KSTEP_BYTES + row * 16;
@@ -1197,6 +1216,8 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                                 const float rr = (v[i] - s_obs[n + i]) * s_isig[n + i];  // isig = 0 on padding
                                 chi = fmaf(rr, rr, chi);
                             }
+                        } else if (DBG & 8) {
+                            if (v[3] == 12345.f) a.out[0] = v[0];
                         } else {
                             // 32x16 transpose through this warp's staging tile (row stride 20 floats: conflict-free
                             // 128-bit writes) -> every store instruction writes two 64-byte row segments
@@ -1208,7 +1229,11 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                             __syncwarp();
                             const float* sp = stage + rsel * 20 + cl;
                             float* op = orow + n;
-                            if (full_tile && n + 16 <= NO) {
+                            if (full_tile && n + 16 <= NO && NO == 451) {
+                                // the reference's 451-bin grid: row offsets are immediates of the store instructions
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) __stcs(op + 2 * i * 451, sp[2 * i * 20]);
+                            } else if (full_tile && n + 16 <= NO) {
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) __stcs(op + static_cast<long long>(2 * i) * NO, sp[2 * i * 20]);
                             } else {

@@ -868,6 +868,143 @@ static int run_timing4() {
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Bulk-tensor (TMA) store probe: an [n, 451] fp32 array described as 4-row super-rows (dim0 = 1804, pitch 7216 B);
+// one box of (W, 8) at element coordinate (x, y) with x NOT a multiple of 4.
+//   umma_probe s <x> <W>
+// ---------------------------------------------------------------------------------------------
+#include <cuda.h>
+__global__ void tma_store_kernel(const __grid_constant__ CUtensorMap map, int x, int y, int W) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* st = reinterpret_cast<float*>(smem);
+    for (int i = threadIdx.x; i < 8 * W; i += blockDim.x) st[i] = 1000.f * (i / W) + (i % W);
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(reinterpret_cast<uint64_t>(&map)),
+                     "r"(smem_u32(smem)), "r"(x), "r"(y) : "memory");
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    }
+}
+static int run_tma_store(int argc, char** argv) {
+    const int x = argc > 2 ? atoi(argv[2]) : 451 + 16, W = argc > 3 ? atoi(argv[3]) : 112, n = 64, NO = 451, y = 2;
+    float* d;
+    CK(cudaMalloc(&d, (size_t)n * NO * 4));
+    CK(cudaMemset(d, 0, (size_t)n * NO * 4));
+    void* fnp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &q));
+    typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                           const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {4ull * NO, (cuuint64_t)(n / 4)};
+    const cuuint64_t strides[1] = {16ull * NO};
+    const cuuint32_t box[2] = {(cuuint32_t)W, 8u};
+    const cuuint32_t es[2] = {1u, 1u};
+    CUresult r = ((Fn)fnp)(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    printf("encode result %d (query %d)\n", (int)r, (int)q);
+    if (r != CUDA_SUCCESS) return 3;
+    tma_store_kernel<<<1, 128, 8 * W * 4 + 1024>>>(map, x, y, W);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("tma store x=%d W=%d: CUDA error %s\n", x, W, cudaGetErrorString(e)); return 2; }
+    std::vector<float> h((size_t)n * NO);
+    CK(cudaMemcpy(h.data(), d, h.size() * 4, cudaMemcpyDeviceToHost));
+    int bad = 0, nz = 0;
+    for (int row = 0; row < n; ++row)
+        for (int c = 0; c < NO; ++c) {
+            // element (x', y') of the super-row view: row = 4 y' + x' / NO, col = x' % NO
+            float want = 0.f;
+            const int yy = row / 4, xx = (row % 4) * NO + c;
+            if (yy >= y && yy < y + 8 && xx >= x && xx < x + W) want = 1000.f * (yy - y) + (xx - x);
+            const float got = h[(size_t)row * NO + c];
+            bad += (got != want);
+            nz += (got != 0.f);
+        }
+    printf("tma store x=%d W=%d: nonzero=%d mismatches=%d  %s\n", x, W, nz, bad, bad == 0 ? "PASS" : "FAIL");
+    return bad ? 3 : 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Hand-off latency probe: warp 0 signals barrier X (mode 0: mbarrier.arrive, 1: tcgen05.commit with no MMA pending,
+// 2: tcgen05.commit right after one MMA N=64), warp 1 waits for X and arrives on Y, warp 0 waits for Y.  Cycles per round trip.
+//   umma_probe p
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+pingpong_kernel(int mode, int rounds, int fences, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t barx, bary;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int e = tid; e < 32 * 1024 / 4; e += 128) reinterpret_cast<uint32_t*>(smem)[e] = 0x3c003c00u;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&barx)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bary)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tm = tmem_base_s;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t da = make_desc(smem_u32(smem), 2048, 128), db = make_desc(smem_u32(smem) + 16384, 64 * 16, 128);
+    if (warp == 0) {
+        const long long t0 = clock64();
+        for (int r = 0; r < rounds; ++r) {
+            if (fences) asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (elect_one()) {
+                if (mode == 2)
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tm),
+                                 "l"(da), "l"(db), "r"(idesc), "r"(1u) : "memory");
+                if (mode == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&barx)) : "memory");
+                else asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&barx)) : "memory");
+            }
+            __syncwarp();
+            mbar_wait(&bary, r & 1, nullptr, 0);
+        }
+        if (lane == 0) out[0] = clock64() - t0;
+    } else if (warp == 1) {
+        for (int r = 0; r < rounds; ++r) {
+            mbar_wait(&barx, r & 1, nullptr, 0);
+            if (fences) {
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            }
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&bary)) : "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512));
+}
+static int run_pingpong() {
+    long long* d;
+    CK(cudaMalloc(&d, 8));
+    CK(cudaFuncSetAttribute(pingpong_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    for (int fences = 0; fences < 2; ++fences)
+        for (int mode = 0; mode < 3; ++mode) {
+            for (int rep = 0; rep < 2; ++rep) {
+                pingpong_kernel<<<1, 128, 48 * 1024>>>(mode, 1000, fences, d);
+                CK(cudaDeviceSynchronize());
+            }
+            long long c = 0;
+            CK(cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost));
+            printf("pingpong mode=%d (%s) fences=%d : %.0f cycles per round trip\n", mode,
+                   mode == 0 ? "arrive" : mode == 1 ? "commit, pipe idle" : "MMA N=64 + commit", fences, (double)c / 1000);
+        }
+    return 0;
+}
+
 static uint16_t to16(float x, int fp16) {
     if (fp16) {
         __half h = __float2half_rn(x);
@@ -904,6 +1041,8 @@ int main(int argc, char** argv) {
     if (argv[1][0] == 't') return run_timing(argc, argv);
     if (argv[1][0] == 'f') return run_f8(argc, argv);
     if (argv[1][0] == 'u') return run_timing4();
+    if (argv[1][0] == 's') return run_tma_store(argc, argv);
+    if (argv[1][0] == 'p') return run_pingpong();
     const int vi = atoi(argv[1]);
     if (vi < 0 || vi >= nvar) return 1;
     const Variant v = table[vi];
