@@ -59,6 +59,9 @@ constexpr int DBG = VAE21_TC_ABLATE;
 __device__ long long g_tc_timing[160][16];  // [cta][0 total, 1..5 operand-ready wait by consuming layer, 6..10 q_empty wait by layer, 11 ring, 12 rendezvous, 13 issue]
 #endif
 constexpr int MAX_SLOTS = 16;
+#ifndef VAE21_TC_DIRECT_ARRIVE
+#define VAE21_TC_DIRECT_ARRIVE 1  // pair kernel: 1 = the follower's epilogue warps arrive on the leader's barriers themselves,
+#endif                            // 0 = they arrive locally and the follower's idle MMA warp forwards one arrival per event
 #ifndef VAE21_TC_KPS
 #define VAE21_TC_KPS 2   // k-steps per ring slot of the CTA-pair kernel (1 or 2; 1 measured slower: 2.05 vs 1.90 ms)
 #endif
@@ -90,6 +93,12 @@ struct Chunk {
     int qbuf;        // 0/1: ring buffer index, -1: in place (stays in TMEM as next layer's operand)
     int nstages;     // weight stages (each 16 k wide, hi+lo) == K/16
     int kps2;        // pair kernel: k-steps per ring slot for this chunk (as many as fit the slot, at most 4)
+    // copies of the owning layer's fields, so the device loops read ONE record per chunk (no dependent constant loads)
+    int idx_in_layer, last_in_layer;
+    int a_src, out_dst, relu;
+    int bias_n0;     // bias_off + n0
+    int src_first, src_count;   // chunks of the producing layer (first chunk of a layer > 0 only, else src_count = 0)
+    float inv_s8;
     unsigned w_off;  // byte offset of the first stage in the weight image
 };
 
@@ -328,6 +337,24 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
         while (S > 1.f && wmax * S > 32768.f) S *= 0.5f;
         P.L[l].inv_s8 = 1.f / S;
     }
+    for (int c = 0; c < nchunks; ++c) {
+        Chunk& C = P.C[c];
+        const Layer& L = P.L[C.layer];
+        C.idx_in_layer = c - L.first_chunk;
+        C.last_in_layer = (c == L.first_chunk + L.nchunks - 1) ? 1 : 0;
+        C.a_src = L.a_src;
+        C.out_dst = L.out_dst;
+        C.relu = L.relu;
+        C.bias_n0 = L.bias_off + C.n0;
+        C.inv_s8 = L.inv_s8;
+        C.src_first = 0;
+        C.src_count = 0;
+        if (C.layer > 0 && C.idx_in_layer == 0) {
+            C.src_first = P.L[C.layer - 1].first_chunk;
+            C.src_count = P.L[C.layer - 1].nchunks;
+        }
+    }
+
     const size_t img2 = P.w_bytes / 2;  // element offset of image 2
     for (int c = 0; c < nchunks; ++c) {
         const Chunk& C = P.C[c];
@@ -564,6 +591,14 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) 
         : "memory");
 }
 // (Default semantics like CUTLASS' ClusterBarrier: a cluster-scope acquire on every probe costs ~400 cycles.)
+// release at cluster scope: what the arriving thread wrote / fenced before is visible to the remote waiter
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(bar),
+        "r"(rank)
+        : "memory");
+}
 __device__ __forceinline__ uint32_t mbar_try_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -731,13 +766,15 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             mbar_init(bar_ring_full(s), (PAIR && leader) ? 2 : 1);
             mbar_init(bar_ring_empty(s), 1);
         }
-        const uint32_t fwd = (PAIR && leader) ? 1u : 0u;  // + one forwarded arrival from the peer CTA
+        // epilogue -> MMA hand-offs: ONE arrival per epilogue warp (elected lane after __syncwarp), not one per thread.  In a
+        // pair the follower's epilogue warps arrive DIRECTLY on the leader's barriers (remote arrive), so those count both CTAs.
+        const uint32_t both = (PAIR && leader && VAE21_TC_DIRECT_ARRIVE) ? 2u : 1u;
+        const uint32_t fwd = (PAIR && leader && !VAE21_TC_DIRECT_ARRIVE) ? 1u : 0u;
         for (int i = 0; i < NFULL; ++i) mbar_init(bar_chunk_full(i), P.issuers);
-        // epilogue -> MMA hand-offs: ONE arrival per epilogue warp (elected lane after __syncwarp), not one per thread
-        for (int b = 0; b < 2; ++b) mbar_init(bar_q_empty(b), NEPI / 32 + fwd);
+        for (int b = 0; b < 2; ++b) mbar_init(bar_q_empty(b), (NEPI / 32) * both + fwd);
         // (chunk_full: one commit from each of the two issuing warps)
-        for (int j = 0; j < MAX_LCHUNK; ++j) mbar_init(bar_act_ready(j), NEPI / 32 + fwd);
-        mbar_init(bar_a0_ready, 4 + fwd);
+        for (int j = 0; j < MAX_LCHUNK; ++j) mbar_init(bar_act_ready(j), (NEPI / 32) * both + fwd);
+        mbar_init(bar_a0_ready, 4 * both + fwd);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (tid < 16) {
@@ -857,11 +894,12 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 mbar_wait(bar, parity);
             } else if (leader) {
                 mbar_wait_cluster(bar, parity);
-            } else {
+            } else if (!VAE21_TC_DIRECT_ARRIVE) {
                 mbar_wait(bar, parity);
                 if (mw == 0 && lane == 0) mbar_arrive_remote(bar, 0);
                 __syncwarp();
             }
+            // (direct mode: the follower's epilogue warps signal the leader themselves; the forwarder only relays ring slots)
         };
         for (long long unit = unit0; unit < nunits; unit += ustep) {
             for (int c = 0; c < n_chunks; ++c) {
@@ -869,18 +907,17 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 const long long t_chunk0 = clock64();
 #endif
                 const Chunk& C = P.C[c];
-                const Layer& L = P.L[C.layer];
                 // Operand readiness is tracked per chunk of the PRODUCING layer: k-step s of this layer only needs
                 // the 16 features [16 s, 16 s + 16), so the first chunk of a layer starts as soon as the first chunk of
                 // the previous layer has been converted and waits for the later ones when it reaches their k range.
                 int src = -1, src_end = -1;  // chunks of the producing layer still to wait for
-                if (c == L.first_chunk) {
+                if (C.idx_in_layer == 0) {
                     if (C.layer == 0) {
                         { TSTART sync_event(bar_a0_ready, a0_cnt & 1u); TADD(tm_evt[0]) }
                         ++a0_cnt;
                     } else {
-                        src = P.L[C.layer - 1].first_chunk;
-                        src_end = src + P.L[C.layer - 1].nchunks;
+                        src = C.src_first;
+                        src_end = src + C.src_count;
                     }
                 }
                 if (C.qbuf >= 0) {  // accumulator buffer must have been drained by the epilogue
@@ -903,8 +940,8 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 const uint32_t b_lo16 = (b_kg * 2u) >> 4;                         // hi tile -> lo tile, in 16 B units
                 // low descriptor words: (address >> 4) | (LBO >> 4) << 16; slots are slot16 apart
                 const uint32_t b_base32 = ((ring0 & 0x3FFFFu) >> 4) | ((b_kg >> 4) << 16);
-                const bool ts = (L.a_src == A_TMEM);
-                uint32_t a_lo32 = (((base + (L.a_src == A_SMEM_A0 ? P.off_a0 : P.off_act)) & 0x3FFFFu) >> 4) | a_lbo;
+                const bool ts = (C.a_src == A_TMEM);
+                uint32_t a_lo32 = (((base + (C.a_src == A_SMEM_A0 ? P.off_a0 : P.off_act)) & 0x3FFFFu) >> 4) | a_lbo;
                 uint32_t ta = tm;
                 const int nst = C.nstages;
                 int next_src_k = (src >= 0) ? 0 : 0x7fffffff;  // k-step at which the next producing chunk starts
@@ -922,7 +959,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                     // the k-steps of this iteration may cross into the next chunk of the producing layer
                     if (s + nk - 1 >= next_src_k) {
                         do {
-                            const int j = src - P.L[C.layer - 1].first_chunk;
+                            const int j = src - C.src_first;
                             { TSTART sync_event(bar_act_ready(j), (act_cnt[j]++) & 1u); TADD(tm_evt[C.layer < 5 ? C.layer : 4]) }
                             ++src;
                             next_src_k = (src < src_end) ? (P.C[src].n0 >> 4) : 0x7fffffff;
@@ -1089,6 +1126,12 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         uint32_t seq = 0;
         uint32_t tcount = 0;
 
+        // hand-off to the MMA issuer, which lives in the leader CTA of a pair
+        auto signal_mma = [&](uint32_t bar) {
+            if (PAIR && !leader && VAE21_TC_DIRECT_ARRIVE == 1) mbar_arrive_remote(bar, 0);
+            else if (PAIR && !leader && VAE21_TC_DIRECT_ARRIVE == 2) mbar_arrive_remote_release(bar, 0);
+            else mbar_arrive(bar);
+        };
         auto write_a0 = [&](long long tile) {
             // fused parameter transform (preprocess.py:74-78, :105-108) in fp32 -- the operand is
             // split to 16-bit hi/lo pairs anyway -- -> layer-0 operand (k padded to 16)
@@ -1129,7 +1172,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             *reinterpret_cast<uint4*>(a0 + 3 * A_KG_BYTES + row * 16) = make_uint4(w[12], w[13], w[14], w[15]);
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_a0_ready);
+            if (lane == 0) signal_mma(bar_a0_ready);
         };
 
         if (half == 0 && unit0 < nunits) write_a0(CG * unit0 + rank);
@@ -1145,16 +1188,15 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             float chi = 0.f;
             for (int c = 0; c < n_chunks; ++c) {
                 const Chunk& C = P.C[c];
-                const Layer& L = P.L[C.layer];
                 mbar_wait(bar_chunk_full(seq & (NFULL - 1)), (seq / NFULL) & 1u);
                 ++seq;
                 tc_fence_after();
-                const float* bl = s_bias + L.bias_off + C.n0;
+                const float* bl = s_bias + C.bias_n0;
                 const int ng = C.ncols / 16;
                 const uint32_t tbase = tm + tlane + static_cast<uint32_t>(C.dcol);
-                const int out_dst = L.out_dst;
-                const bool do_relu = L.relu != 0;
-                const float inv_s8 = (FMT == 2) ? L.inv_s8 : 1.f;
+                const int out_dst = C.out_dst;
+                const bool do_relu = C.relu != 0;
+                const float inv_s8 = (FMT == 2) ? C.inv_s8 : 1.f;
                 auto process = [&](uint32_t (&r)[16], int g) {
                     const uint32_t taddr = tbase + static_cast<uint32_t>(16 * g);
                     if (out_dst != DST_FINAL) {
@@ -1268,10 +1310,10 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 tc_fence_before();
                 __syncwarp();  // every lane's writes / reads are done and fenced before the elected lane signals
                 if (lane == 0) {
-                    if (C.qbuf >= 0) mbar_arrive(bar_q_empty(C.qbuf));
-                    if (out_dst != DST_FINAL) mbar_arrive(bar_act_ready(c - L.first_chunk));
+                    if (C.qbuf >= 0) signal_mma(bar_q_empty(C.qbuf));
+                    if (out_dst != DST_FINAL) signal_mma(bar_act_ready(C.idx_in_layer));
                 }
-                const bool last_of_layer = (c == L.first_chunk + L.nchunks - 1);
+                const bool last_of_layer = C.last_in_layer != 0;
                 // the layer-0 operand of the NEXT tile can be written as soon as layer 0 of this tile is done
                 if (half == 0 && C.layer == 0 && last_of_layer) {
                     if (unit + ustep < nunits) write_a0(CG * (unit + ustep) + rank);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: batched DirectEmulator.predict, 451 z-bins, 1M-row batch per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16x3|fp16x3|fp32] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp16e4m3|bf16x3|fp16x3|fp32] [--impl reference]
 
 One "step" = one pass of the fused kernel over one batch of `--rows` synthetic parameter vectors
 (default 1,000,000 per GPU: BASELINE.json configs[1]) drawn from the prior ranges, the full
@@ -33,7 +33,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FLOP_PER_SIGNAL = 740_608          # 2 * 370,304 MAC
-EXEC_MAC_PER_SIGNAL_TC = 3 * 375_808   # 3 split passes, K/N padding of the MMA shapes
+PADDED_MAC_PER_SIGNAL = 375_808        # K/N padding of the MMA shapes
+# tensor-pipe passes per k-step in units of one kind::f16 MMA: the hi/lo splits issue 3 of them; fp16e4m3 issues one
+# kind::f16 MMA plus one kind::f8f6f4 MMA (K = 32) that takes the same pipe time (measured: profiles/r1_umma_probe_f8.log)
+TC_PASSES = {"bf16x3": 3, "fp16x3": 3, "fp16e4m3": 2}
 BYTES_PER_SIGNAL_F64 = 56 + 1804   # fp64 parameters in, 451 fp32 out
 METRIC = "signals/sec (451 z-bins) @1M batch"
 UNIT = "signals/s"
@@ -253,7 +256,7 @@ def main():
     tc = h.info()["tc_supported"]
     prec_name = args.precision
     if prec_name == "auto":
-        prec_name = "bf16x3" if tc else "fp32"
+        prec_name = "fp16e4m3" if tc else "fp32"  # fastest path inside the north-star tolerance (0.01 mK rms / 0.05 mK max)
     prec = L.PRECISIONS[prec_name]
 
     n = args.rows
@@ -338,12 +341,13 @@ def main():
             ach = per_gpu_rate * FLOP_PER_SIGNAL / 1e12
             roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": ach / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " (burst, cuBLAS bf16)",
-                    "frac_executed": per_gpu_rate * 2 * EXEC_MAC_PER_SIGNAL_TC / 1e12 / pk["bf16_tflops"],
-                    "frac_executed_of_sustained": (per_gpu_rate * 2 * EXEC_MAC_PER_SIGNAL_TC / 1e12 / pk["bf16_tflops_sustained"]
-                                                   if pk.get("bf16_tflops_sustained") else None),
+                    "frac_executed": per_gpu_rate * 2 * TC_PASSES[prec_name] * PADDED_MAC_PER_SIGNAL / 1e12 / pk["bf16_tflops"],
+                    "frac_executed_of_sustained": (per_gpu_rate * 2 * TC_PASSES[prec_name] * PADDED_MAC_PER_SIGNAL / 1e12
+                                                   / pk["bf16_tflops_sustained"] if pk.get("bf16_tflops_sustained") else None),
+                    "passes": TC_PASSES[prec_name],
                     "hbm_gbs_achieved": per_gpu_rate * BYTES_PER_SIGNAL_F64 / 1e9,
-                    "note": "achieved = algorithmic 740,608 FLOP/signal; frac_executed counts the 3 split passes "
-                            "and MMA-shape padding actually issued to the tensor pipe"}
+                    "note": "achieved = algorithmic 740,608 FLOP/signal; frac_executed counts the tensor-pipe passes per k-step "
+                            "(in kind::f16-MMA units, see `passes`) and the MMA-shape padding actually issued"}
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tp):
             roof["traffic"] = json.load(open(tp)).get(prec_name)
@@ -359,7 +363,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16x3": "bf16x3 split, f32 accumulate", "fp16x3": "fp16x3 split, f32 accumulate"}[prec_name],
+            "dtype": {"fp32": "f32", "bf16x3": "bf16x3 split, f32 accumulate", "fp16x3": "fp16x3 split, f32 accumulate",
+                      "fp16e4m3": "fp16 + e4m3 first-order corrections, f32 accumulate"}[prec_name],
             "data": "synthetic",
             "config": {"workload": "DirectEmulator.predict 7->288->352->288->224->451, full 451-bin output to HBM",
                        "rows_per_gpu": n, "params_dtype": "f64", "precision_path": prec_name,
