@@ -28,6 +28,8 @@ EXPORTS = [
     "vae21_version", "vae21_last_error", "vae21_device_count", "vae21_create", "vae21_destroy",
     "vae21_set_model", "vae21_set_norm", "vae21_predict", "vae21_forward_normalised", "vae21_chi2",
     "vae21_host_alloc", "vae21_host_free", "vae21_host_trim", "vae21_get_info", "vae21_time_predict",
+    "vae21_trainer_create", "vae21_trainer_destroy", "vae21_trainer_num_params", "vae21_trainer_set_params",
+    "vae21_trainer_get_params", "vae21_trainer_forward_backward", "vae21_trainer_adam", "vae21_trainer_launches",
 ]
 
 
@@ -72,6 +74,14 @@ def load() -> C.CDLL:
         lib.vae21_host_trim.restype = None
         lib.vae21_get_info.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_float), C.POINTER(i32)]
         lib.vae21_time_predict.argtypes = [vp, vp, i32, i64, vp, i32, i32, C.POINTER(C.c_float)]
+        lib.vae21_trainer_create.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(i32), i32, C.POINTER(vp)]
+        lib.vae21_trainer_destroy.argtypes = [vp]
+        lib.vae21_trainer_num_params.argtypes = [vp, C.POINTER(i64)]
+        lib.vae21_trainer_set_params.argtypes = [vp, f32p, i32]
+        lib.vae21_trainer_get_params.argtypes = [vp, f32p]
+        lib.vae21_trainer_forward_backward.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, vp, vp, vp]
+        lib.vae21_trainer_adam.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp]
+        lib.vae21_trainer_launches.argtypes = [vp, C.POINTER(i64)]
         for name in EXPORTS:
             fn = getattr(lib, name)
             if fn.restype is C.c_int and name not in ("vae21_version",):
@@ -285,3 +295,70 @@ class Handle:
         _check(self._lib.vae21_time_predict(self._h, ptr, F64 if dt == np.float64 else F32, n, optr, int(precision),
                                             int(iters), C.byref(ms)))
         return ms.value
+
+
+# ---- trainer ---------------------------------------------------------------------------------
+
+
+class Trainer:
+    """ctypes face of `vae21_trainer` (include/vae21.h): fp32 parameters + Adam moments of a Dense stack on one GPU.
+    Device buffers are passed as anything `_unwrap` understands (torch CUDA tensors, __cuda_array_interface__)."""
+
+    def __init__(self, dims, relu, max_batch=256, device=0):
+        self._lib = load()
+        self.dims = [int(d) for d in dims]
+        self.relu = [int(bool(r)) for r in relu]
+        self.device = int(device)
+        self.max_batch = int(max_batch)
+        h = C.c_void_p()
+        n = len(self.dims) - 1
+        _check(self._lib.vae21_trainer_create(self.device, n, (C.c_int32 * (n + 1))(*self.dims), (C.c_int32 * n)(*self.relu),
+                                              self.max_batch, C.byref(h)))
+        self._t = h
+        cnt = C.c_int64(0)
+        _check(self._lib.vae21_trainer_num_params(self._t, C.byref(cnt)))
+        self.num_params = int(cnt.value)
+        self._fin = weakref.finalize(self, self._lib.vae21_trainer_destroy, h)
+
+    def close(self):
+        self._fin()
+
+    def set_params(self, flat, reset_moments=True):
+        flat = np.ascontiguousarray(flat, dtype=np.float32)
+        if flat.size != self.num_params:
+            raise ValueError(f"expected {self.num_params} parameters, got {flat.size}")
+        _check(self._lib.vae21_trainer_set_params(self._t, flat.ctypes.data_as(C.POINTER(C.c_float)), int(bool(reset_moments))))
+
+    def get_params(self) -> np.ndarray:
+        out = np.empty(self.num_params, np.float32)
+        _check(self._lib.vae21_trainer_get_params(self._t, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    @staticmethod
+    def _dev_ptr(obj, dtype, what):
+        if obj is None:
+            return None
+        ptr, dev, _, dt, _, _ = _unwrap(obj)
+        if not dev:
+            raise ValueError(f"{what} must be a device buffer")
+        if np.dtype(dt) != np.dtype(dtype):
+            raise ValueError(f"{what} must be {np.dtype(dtype).name}, got {np.dtype(dt).name}")
+        return ptr
+
+    def forward_backward(self, x_all, y_all, w_all, batch, grad_scale, grad, loss_sum, idx=None, first=0, stream=None):
+        """One batch: rows idx[0:batch] (int32 device array) or first..first+batch of the resident set.
+        grad=None: forward + loss only.  loss_sum (1-element float32 device buffer) is incremented."""
+        _check(self._lib.vae21_trainer_forward_backward(
+            self._t, self._dev_ptr(x_all, np.float32, "x_all"), self._dev_ptr(y_all, np.float32, "y_all"),
+            self._dev_ptr(w_all, np.float32, "w_all"), self._dev_ptr(idx, np.int32, "idx"), int(first), int(batch),
+            float(grad_scale), self._dev_ptr(grad, np.float32, "grad"), self._dev_ptr(loss_sum, np.float32, "loss_sum"),
+            C.c_void_p(int(stream)) if stream else None))
+
+    def adam(self, grad, lr_t, beta1=0.9, beta2=0.999, eps=1e-7, stream=None):
+        _check(self._lib.vae21_trainer_adam(self._t, self._dev_ptr(grad, np.float32, "grad"), float(lr_t), float(beta1),
+                                            float(beta2), float(eps), C.c_void_p(int(stream)) if stream else None))
+
+    def launches(self) -> int:
+        n = C.c_int64(0)
+        _check(self._lib.vae21_trainer_launches(self._t, C.byref(n)))
+        return int(n.value)

@@ -1,0 +1,166 @@
+// C-ABI of the trainer (declared in include/vae21.h).  Included by vae21_api.cu.
+#pragma once
+#include <vector>
+
+#include "train_kernels.cuh"
+
+struct vae21_trainer {
+    int device = 0;
+    int n_layers = 0;
+    int dims[VAE21_MAX_LAYERS + 1] = {0};
+    int relu[VAE21_MAX_LAYERS] = {0};
+    int max_batch = 0;
+    long long n_params = 0;
+    long long w_off[VAE21_MAX_LAYERS] = {0}, b_off[VAE21_MAX_LAYERS] = {0};  // float offsets into the flat parameter vector
+    float *p = nullptr, *m = nullptr, *v = nullptr;                           // parameters and Adam moments [n_params]
+    float* act[VAE21_MAX_LAYERS + 1] = {nullptr};                             // act[0] = batch inputs, act[l+1] = output of layer l
+    float* delta[2] = {nullptr, nullptr};                                     // ping-pong dL/d(pre-activation... post-mask) buffers
+    float *yb = nullptr, *wb = nullptr, *loss_rows = nullptr;
+    long long launches = 0;
+};
+
+namespace {
+int trainer_use(vae21_trainer* t) {
+    if (!t) return fail(VAE21_ERR_ARG, "null trainer");
+    CK(cudaSetDevice(t->device));
+    return 0;
+}
+void trainer_forward(vae21_trainer* t, int batch, cudaStream_t st) {
+    for (int l = 0; l < t->n_layers; ++l) {
+        const int K = t->dims[l], N = t->dims[l + 1];
+        trk::sgemm_kernel<0><<<trk::grid_for(batch, N), 256, 0, st>>>(batch, N, K, t->act[l], K, t->p + t->w_off[l], N, t->act[l + 1], N,
+                                                                      t->p + t->b_off[l], t->relu[l], nullptr, 0);
+        t->launches++;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int vae21_trainer_create(int device, int n_layers, const int* dims, const int* relu_flags, int max_batch, vae21_trainer** out) {
+    if (!dims || !relu_flags || !out) return fail(VAE21_ERR_ARG, "null argument");
+    if (n_layers < 1 || n_layers > VAE21_MAX_LAYERS || max_batch < 1) return fail(VAE21_ERR_ARG, "bad n_layers / max_batch");
+    int count = 0;
+    CK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(VAE21_ERR_ARG, "device %d out of range (%d visible)", device, count);
+    CK(cudaSetDevice(device));
+    vae21_trainer* t = new vae21_trainer();
+    t->device = device;
+    t->n_layers = n_layers;
+    t->max_batch = max_batch;
+    long long off = 0;
+    int widest = 0;
+    for (int l = 0; l <= n_layers; ++l) {
+        if (dims[l] < 1) { delete t; return fail(VAE21_ERR_ARG, "dims[%d] = %d", l, dims[l]); }
+        t->dims[l] = dims[l];
+        widest = dims[l] > widest ? dims[l] : widest;
+    }
+    for (int l = 0; l < n_layers; ++l) {
+        t->relu[l] = relu_flags[l] ? 1 : 0;
+        t->w_off[l] = off;
+        off += static_cast<long long>(dims[l]) * dims[l + 1];
+        t->b_off[l] = off;
+        off += dims[l + 1];
+    }
+    t->n_params = off;
+    for (float** q : {&t->p, &t->m, &t->v}) {
+        CK(cudaMalloc(q, sizeof(float) * off));
+        CK(cudaMemset(*q, 0, sizeof(float) * off));
+    }
+    for (int l = 0; l <= n_layers; ++l) CK(cudaMalloc(&t->act[l], sizeof(float) * static_cast<size_t>(max_batch) * dims[l]));
+    for (int i = 0; i < 2; ++i) CK(cudaMalloc(&t->delta[i], sizeof(float) * static_cast<size_t>(max_batch) * widest));
+    CK(cudaMalloc(&t->yb, sizeof(float) * static_cast<size_t>(max_batch) * dims[n_layers]));
+    CK(cudaMalloc(&t->wb, sizeof(float) * max_batch));
+    CK(cudaMalloc(&t->loss_rows, sizeof(float) * max_batch));
+    *out = t;
+    return 0;
+}
+
+int vae21_trainer_destroy(vae21_trainer* t) {
+    if (!t) return 0;
+    cudaSetDevice(t->device);
+    cudaDeviceSynchronize();
+    for (float* q : {t->p, t->m, t->v, t->delta[0], t->delta[1], t->yb, t->wb, t->loss_rows})
+        if (q) cudaFree(q);
+    for (int l = 0; l <= t->n_layers; ++l)
+        if (t->act[l]) cudaFree(t->act[l]);
+    delete t;
+    return 0;
+}
+
+int vae21_trainer_num_params(vae21_trainer* t, int64_t* n) {
+    if (!t || !n) return fail(VAE21_ERR_ARG, "null argument");
+    *n = t->n_params;
+    return 0;
+}
+
+int vae21_trainer_set_params(vae21_trainer* t, const float* flat_host, int reset_moments) {
+    if (int rc = trainer_use(t)) return rc;
+    if (!flat_host) return fail(VAE21_ERR_ARG, "null parameters");
+    CK(cudaMemcpy(t->p, flat_host, sizeof(float) * t->n_params, cudaMemcpyHostToDevice));
+    if (reset_moments) {
+        CK(cudaMemset(t->m, 0, sizeof(float) * t->n_params));
+        CK(cudaMemset(t->v, 0, sizeof(float) * t->n_params));
+    }
+    return 0;
+}
+
+int vae21_trainer_get_params(vae21_trainer* t, float* flat_host) {
+    if (int rc = trainer_use(t)) return rc;
+    if (!flat_host) return fail(VAE21_ERR_ARG, "null output");
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(flat_host, t->p, sizeof(float) * t->n_params, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int vae21_trainer_forward_backward(vae21_trainer* t, const float* x_all, const float* y_all, const float* w_all, const int* idx, int64_t first,
+                                   int batch, float grad_scale, float* grad, float* loss_sum, void* stream) {
+    if (int rc = trainer_use(t)) return rc;
+    if (!x_all || !y_all || !w_all || !loss_sum) return fail(VAE21_ERR_ARG, "null device pointer");
+    if (batch < 1 || batch > t->max_batch) return fail(VAE21_ERR_ARG, "batch %d outside [1,%d]", batch, t->max_batch);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int L = t->n_layers, NO = t->dims[L];
+    trk::gather_kernel<<<batch, 128, 0, st>>>(x_all, y_all, w_all, idx, first, batch, t->dims[0], NO, t->act[0], t->yb, t->wb);
+    trainer_forward(t, batch, st);
+    float* d_cur = t->delta[0];
+    trk::loss_delta_kernel<<<(batch + 7) / 8, 256, 0, st>>>(t->act[L], t->yb, t->wb, batch, NO, grad_scale, grad ? d_cur : nullptr, t->loss_rows);
+    trk::loss_sum_kernel<<<1, 32, 0, st>>>(t->loss_rows, batch, loss_sum);
+    t->launches += 3;
+    if (grad) {
+        for (int l = L - 1; l >= 0; --l) {
+            const int K = t->dims[l], N = t->dims[l + 1];
+            trk::colsum_kernel<<<(N + 127) / 128, 128, 0, st>>>(d_cur, batch, N, grad + t->b_off[l]);
+            trk::sgemm_kernel<2><<<trk::grid_for(K, N), 256, 0, st>>>(K, N, batch, t->act[l], K, d_cur, N, grad + t->w_off[l], N, nullptr, 0, nullptr, 0);
+            t->launches += 2;
+            if (l > 0) {
+                float* d_next = (d_cur == t->delta[0]) ? t->delta[1] : t->delta[0];
+                // dL/d(pre-activation of layer l-1) = (D W_l^T) masked by the ReLU of layer l-1 (its output is act[l])
+                trk::sgemm_kernel<1><<<trk::grid_for(batch, K), 256, 0, st>>>(batch, K, N, d_cur, N, t->p + t->w_off[l], N, d_next, K, nullptr, 0,
+                                                                              t->relu[l - 1] ? t->act[l] : nullptr, K);
+                t->launches++;
+                d_cur = d_next;
+            }
+        }
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int vae21_trainer_adam(vae21_trainer* t, const float* grad, float lr_t, float beta1, float beta2, float eps, void* stream) {
+    if (int rc = trainer_use(t)) return rc;
+    if (!grad) return fail(VAE21_ERR_ARG, "null gradient");
+    const long long n = t->n_params;
+    trk::adam_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(t->p, t->m, t->v, grad, n, lr_t, beta1,
+                                                                                                            beta2, eps);
+    t->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int vae21_trainer_launches(vae21_trainer* t, int64_t* n) {
+    if (!t || !n) return fail(VAE21_ERR_ARG, "null argument");
+    *n = t->launches;
+    return 0;
+}
+
+}  // extern "C"

@@ -551,3 +551,5 @@ int vae21_debug_tc_timing(long long* out) { return tck::read_timing(out) == cuda
 #endif
 
 }  // extern "C"
+
+#include "train_api.cuh"

@@ -310,10 +310,52 @@ class DirectEmulator:
     def save(self):
         raise NotImplementedError("Not implemented yet.")
 
-    def train(self, epochs, callbacks=[], verbose="tqdm"):  # noqa: B006 - signature of the reference
-        raise NotImplementedError(
-            "training (emulator.py:339-381) is outside the B200 hot path built so far; train with the "
-            "reference and load the weights with load_model()")
+    def train(self, epochs, callbacks=[], verbose="tqdm", *, seed=None, distributed=False):  # noqa: B006 - reference signature
+        """Train the emulator (emulator.py:339-381): batches of 256, Adam and the relative-MSE loss of
+        ``relative_mse_loss(signal_train)``, validation on the validation set after every epoch.
+
+        ``callbacks`` are objects of ``training.EarlyStopping`` / ``training.ReduceLROnPlateau`` (same constructor
+        arguments as the tf.keras callbacks of notebooks/Training.ipynb; TensorFlow objects are not accepted -- there is no
+        TensorFlow here).  The optimiser comes from ``self.emulator.compile(optimizer=training.Adam(0.01), loss=...)``;
+        without ``compile`` Adam with the Keras default learning rate 1e-3 is used.  ``verbose="tqdm"`` maps to one line per
+        epoch.  Extra keywords: ``seed`` fixes the shuffling, ``distributed=True`` splits every batch over the ranks of an
+        initialised torch.distributed group (gradient all-reduce over NCCL).
+
+        Returns (loss, val_loss): per-epoch training and validation losses, like the reference."""
+        from . import training as tr
+
+        if self.par_train is None or self.signal_train is None:
+            raise ValueError("training needs par_train / signal_train (this emulator was built from NormStats only)")
+        x_train = pp.par_transform(self.par_train, self.par_train).astype(np.float32)
+        y_train = pp.preproc(np.asarray(self.signal_train), self.signal_train).astype(np.float32)
+        loss_fn_mean = (np.mean(self.signal_train, axis=0) / np.std(self.signal_train)).astype(np.float32)
+        amp_w = lambda y: (1.0 / np.max(np.abs(y + loss_fn_mean), axis=1) ** 2).astype(np.float32)  # noqa: E731 (emulator.py:70-80)
+        x_val = y_val = w_val = None
+        if self.par_val is not None and self.signal_val is not None and len(self.par_val):
+            x_val = pp.par_transform(self.par_val, self.par_train).astype(np.float32)
+            y_val = pp.preproc(np.asarray(self.signal_val), self.signal_train).astype(np.float32)
+            w_val = amp_w(y_val)
+        compiled = self.emulator._compiled or {}
+        opt = compiled.get("optimizer")
+        if opt is None:
+            opt = tr.Adam()
+        elif not isinstance(opt, tr.Adam):
+            lr = getattr(opt, "learning_rate", getattr(opt, "lr", None))
+            if lr is None:
+                raise TypeError("optimizer must be training.Adam or expose .learning_rate")
+            opt = tr.Adam(float(lr))
+        w = self.emulator.weights
+        flat, hist = tr.fit(w.dims, w.relu, tr.flatten_weights(w.kernels, w.biases), x_train, y_train, amp_w(y_train), x_val, y_val,
+                            w_val, optimizer=opt, epochs=epochs, batch_size=256, callbacks=list(callbacks), seed=seed,
+                            device=self.device, distributed=distributed, verbose=1 if verbose in ("tqdm", 1, 2) else 0)
+        ks, bs = tr.unflatten_weights(flat, w.dims)
+        arrays = []
+        for k, b in zip(ks, bs):
+            arrays += [k, b]
+        self.emulator.set_weights(arrays)
+        self._norm_for = None
+        self.last_training = hist
+        return hist["loss"], hist["val_loss"]
 
     # -- evaluation ----------------------------------------------------------------------------
     def _handle(self) -> _lib.Handle:

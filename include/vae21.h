@@ -138,6 +138,30 @@ int vae21_get_info(vae21_handle* h, int64_t* kernel_launches, float* last_kernel
 int vae21_time_predict(vae21_handle* h, const void* params_dev, int params_dtype, int64_t n, float* out_dev,
                        int precision, int iters, float* ms_per_launch);
 
+/*
+ * ---- training (replaces the Keras `fit` behind DirectEmulator.train, emulator.py:339-381) ---------------
+ * A trainer owns the fp32 parameters of a Dense stack in Keras `get_weights()` order (per layer: kernel
+ * [in,out] row-major, then bias), the Adam moments, and batch workspaces.  One optimisation step is
+ *   forward_backward (gathers the batch rows idx[0..batch) -- or first..first+batch when idx is NULL -- from the
+ *   device-resident set, runs forward + relative-MSE loss (emulator.py:51-83: per-sample MSE times w_i = 1/amp_i^2)
+ *   + backward; writes the gradient of (sum over the batch of loss_i) * n_out * grad_scale ... i.e. with
+ *   grad_scale = 1 / (n_out * global_batch) the gradient of the global-batch mean loss restricted to these rows)
+ *   [all-reduce `grad` over the data-parallel ranks here]
+ *   adam (Keras semantics; lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) is computed by the caller).
+ * loss_sum (device, 1 float) is incremented by sum_i loss_i.  grad == NULL: forward + loss only (validation).
+ * All pointers except `out`/`n`/flat_host are DEVICE pointers.
+ */
+typedef struct vae21_trainer vae21_trainer;
+int vae21_trainer_create(int device, int n_layers, const int* dims, const int* relu_flags, int max_batch, vae21_trainer** out);
+int vae21_trainer_destroy(vae21_trainer* t);
+int vae21_trainer_num_params(vae21_trainer* t, int64_t* n);
+int vae21_trainer_set_params(vae21_trainer* t, const float* flat_host, int reset_moments);
+int vae21_trainer_get_params(vae21_trainer* t, float* flat_host);
+int vae21_trainer_forward_backward(vae21_trainer* t, const float* x_all, const float* y_all, const float* w_all, const int* idx,
+                                   int64_t first, int batch, float grad_scale, float* grad, float* loss_sum, void* stream);
+int vae21_trainer_adam(vae21_trainer* t, const float* grad, float lr_t, float beta1, float beta2, float eps, void* stream);
+int vae21_trainer_launches(vae21_trainer* t, int64_t* n);
+
 #ifdef __cplusplus
 }
 #endif
