@@ -17,6 +17,8 @@ a single device, and all ranks apply the same Adam update (parameters stay bit-i
 from __future__ import annotations
 
 import math
+import os
+import time
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -165,6 +167,7 @@ def fit(dims: Sequence[int], relu: Sequence[int], flat_params: np.ndarray, x, y,
     rng = np.random.default_rng(seed)
     state = FitState(tr, optimizer)
     hist = {"loss": [], "val_loss": [], "lr": []}
+    timing = {"allreduce_s": 0.0} if os.environ.get("VAE21_TRAIN_TIMING") else None
     for cb in callbacks:
         cb.on_train_begin(state)
     for epoch in range(int(epochs)):
@@ -183,7 +186,13 @@ def fit(dims: Sequence[int], relu: Sequence[int], flat_params: np.ndarray, x, y,
             else:
                 grad.zero_()
             if distributed and world > 1:
+                if timing is not None:
+                    torch.cuda.synchronize()
+                    t_a = time.perf_counter()
                 dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+                if timing is not None:
+                    torch.cuda.synchronize()
+                    timing["allreduce_s"] += time.perf_counter() - t_a
             optimizer.iterations += 1
             t = optimizer.iterations
             lr_t = optimizer.learning_rate * math.sqrt(1.0 - optimizer.beta_2**t) / (1.0 - optimizer.beta_1**t)
@@ -212,6 +221,8 @@ def fit(dims: Sequence[int], relu: Sequence[int], flat_params: np.ndarray, x, y,
         cb.on_train_end(state)
     out = tr.get_params()
     hist["kernel_launches"] = tr.launches()
+    if timing is not None:
+        hist["timing"] = timing
     tr.close()
     return out, hist
 
