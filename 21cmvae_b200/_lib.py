@@ -26,7 +26,7 @@ PRECISIONS = {"fp32": FP32_SIMT, "fp32_simt": FP32_SIMT, "tc": TC_BF16X3, "bf16x
 
 EXPORTS = [
     "vae21_version", "vae21_last_error", "vae21_device_count", "vae21_create", "vae21_destroy",
-    "vae21_set_model", "vae21_set_norm", "vae21_predict", "vae21_forward_normalised", "vae21_chi2",
+    "vae21_set_model", "vae21_set_norm", "vae21_predict", "vae21_forward_normalised", "vae21_chi2", "vae21_chi2_grid",
     "vae21_host_alloc", "vae21_host_free", "vae21_host_trim", "vae21_get_info", "vae21_time_predict",
     "vae21_trainer_create", "vae21_trainer_destroy", "vae21_trainer_num_params", "vae21_trainer_set_params",
     "vae21_trainer_get_params", "vae21_trainer_forward_backward", "vae21_trainer_adam", "vae21_trainer_launches",
@@ -67,6 +67,8 @@ def load() -> C.CDLL:
         lib.vae21_forward_normalised.argtypes = [vp, vp, i32, i64, vp, i32, i32, vp]
         lib.vae21_chi2.argtypes = [vp, vp, i32, i32, i64, f32p, f32p, vp, i32, C.POINTER(C.c_float),
                                    C.POINTER(i64), i32, vp]
+        lib.vae21_chi2_grid.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(C.c_double), C.POINTER(C.c_double), i64, i64, f32p, f32p, vp,
+                                        C.POINTER(C.c_float), C.POINTER(i64), i32, vp]
         lib.vae21_host_alloc.argtypes = [C.c_size_t]
         lib.vae21_host_alloc.restype = vp
         lib.vae21_host_free.argtypes = [vp]
@@ -285,6 +287,36 @@ class Handle:
             isg.ctypes.data_as(C.POINTER(C.c_float)), optr, int(odev), C.byref(bv) if want_best else None,
             C.byref(bi) if want_best else None, int(precision), self._stream_ptr(stream, dev and bool(odev), keep)))
         return out, (bv.value if want_best else None), (bi.value if want_best else None)
+
+    def chi2_grid(self, npts, obs, inv_sigma, x_lo=None, x_hi=None, first=0, count=None, out=None, precision=FP32_SIMT, stream=None):
+        """Fused chi^2 over points [first, first + count) of a regular grid in normalised coordinates generated on the device
+        (C order, last dimension fastest).  `out`: optional float32 DEVICE buffer of `count` elements.  Returns (best chi^2, global
+        grid index of the best point)."""
+        if self.dims is None:
+            raise Vae21Error(2, "model not set")
+        nd, nout = self.dims[0], self.dims[-1]
+        npts = [int(v) for v in (npts if np.ndim(npts) else [npts] * nd)]
+        if len(npts) != nd:
+            raise ValueError(f"npts must have {nd} entries")
+        total = int(np.prod(npts, dtype=np.int64))
+        count = total - int(first) if count is None else int(count)
+        lo = np.ascontiguousarray(np.broadcast_to(-1.0 if x_lo is None else np.asarray(x_lo, np.float64), (nd,)), dtype=np.float64)
+        hi = np.ascontiguousarray(np.broadcast_to(1.0 if x_hi is None else np.asarray(x_hi, np.float64), (nd,)), dtype=np.float64)
+        obs = np.ascontiguousarray(obs, dtype=np.float32)
+        isg = np.ascontiguousarray(np.broadcast_to(np.asarray(inv_sigma, dtype=np.float32), (nout,)))
+        if obs.shape != (nout,):
+            raise ValueError(f"obs must have shape ({nout},)")
+        optr, keep = None, None
+        if out is not None:
+            optr, dev, shape, dt, _, keep = _unwrap(out, want_write=True)
+            if not dev or np.dtype(dt) != np.float32 or int(np.prod(shape)) < count:
+                raise ValueError("out must be a float32 device buffer with at least `count` elements")
+        bv, bi = C.c_float(float("nan")), C.c_int64(-1)
+        _check(self._lib.vae21_chi2_grid(
+            self._h, nd, (C.c_int32 * nd)(*npts), lo.ctypes.data_as(C.POINTER(C.c_double)), hi.ctypes.data_as(C.POINTER(C.c_double)),
+            int(first), count, obs.ctypes.data_as(C.POINTER(C.c_float)), isg.ctypes.data_as(C.POINTER(C.c_float)), optr, C.byref(bv),
+            C.byref(bi), int(precision), C.c_void_p(int(stream)) if stream else None))
+        return bv.value, bi.value
 
     def time_predict(self, params_dev, out_dev, precision=FP32_SIMT, iters=10) -> float:
         ptr, dev, n, dt, keep = self._prep_in(params_dev, self.dims[0])

@@ -7,7 +7,7 @@
 #define VAE21_MAX_PAR 16
 
 // what the kernel reads
-enum : int { IN_PARAMS_F32 = 0, IN_PARAMS_F64 = 1, IN_NORMALISED_F32 = 2 };
+enum : int { IN_PARAMS_F32 = 0, IN_PARAMS_F64 = 1, IN_NORMALISED_F32 = 2, IN_GRID = 3 };
 // what the kernel writes
 enum : int { OUT_PREDICT = 0, OUT_NORMALISED = 1, OUT_CHI2 = 2 };
 
@@ -36,7 +36,22 @@ struct LaunchArgs {
     long long row_base;  // global index of row 0 (for argmin)
     int in_mode;
     int out_mode;
+    // IN_GRID: no input array -- row r is point (row_base + r) of a regular grid in NORMALISED coordinates, C order (last
+    // dimension fastest): x_j = grid_lo[j] + i_j * grid_step[j], i_j in [0, grid_n[j])
+    int grid_n[VAE21_MAX_PAR];
+    float grid_lo[VAE21_MAX_PAR];
+    float grid_step[VAE21_MAX_PAR];
 };
+
+// coordinate j of grid point `idx` (see LaunchArgs)
+__device__ __forceinline__ void grid_point(const LaunchArgs& a, unsigned long long idx, int n_dim, float* x) {
+    for (int j = n_dim - 1; j >= 0; --j) {
+        const unsigned long long q = idx / static_cast<unsigned>(a.grid_n[j]);
+        const unsigned i = static_cast<unsigned>(idx - q * static_cast<unsigned>(a.grid_n[j]));
+        x[j] = fmaf(static_cast<float>(i), a.grid_step[j], a.grid_lo[j]);
+        idx = q;
+    }
+}
 
 // ---- device helpers ---------------------------------------------------------
 

@@ -222,7 +222,11 @@ vae21_fp32_kernel(const Model m, const NormConsts nc, const LaunchArgs a, const 
                         x = transform_param(reinterpret_cast<const double*>(a.in)[g], c, nc, false);
                     else if (a.in_mode == IN_PARAMS_F32)
                         x = transform_param(static_cast<double>(reinterpret_cast<const float*>(a.in)[g]), c, nc, true);
-                    else
+                    else if (a.in_mode == IN_GRID) {
+                        float xs[VAE21_MAX_PAR];
+                        grid_point(a, static_cast<unsigned long long>(a.row_base + row), K0, xs);
+                        x = xs[c];
+                    } else
                         x = reinterpret_cast<const float*>(a.in)[g];
                 }
             } else {  // zero the k padding rows

@@ -1139,7 +1139,9 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             float x[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) x[j] = 0.f;
-            if (grow < a.n) {
+            if (grow < a.n && a.in_mode == IN_GRID) {
+                grid_point(a, static_cast<unsigned long long>(a.row_base + grow), K0, x);
+            } else if (grow < a.n) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     if (j < K0) {

@@ -516,6 +516,60 @@ void* vae21_host_alloc(size_t bytes) {
 void vae21_host_free(void* p) { g_pool.release(p); }
 void vae21_host_trim(void) { g_pool.trim(); }
 
+int vae21_chi2_grid(vae21_handle* h, int n_dim, const int* npts, const double* x_lo, const double* x_hi, int64_t first, int64_t count,
+                    const float* obs, const float* inv_sigma, float* chi2_dev, float* best_val, int64_t* best_idx, int precision,
+                    void* stream) {
+    if (!h || !npts || !x_lo || !x_hi) return fail(VAE21_ERR_ARG, "null argument");
+    if (!h->model_set || !h->norm_set) return fail(VAE21_ERR_STATE, "vae21_set_model / vae21_set_norm have not been called");
+    if (n_dim != h->dims[0]) return fail(VAE21_ERR_ARG, "grid has %d dimensions, the model %d inputs", n_dim, h->dims[0]);
+    if (!obs || !inv_sigma) return fail(VAE21_ERR_ARG, "obs / inv_sigma must not be null");
+    double total = 1.0;
+    for (int j = 0; j < n_dim; ++j) {
+        if (npts[j] < 1) return fail(VAE21_ERR_ARG, "npts[%d] = %d", j, npts[j]);
+        total *= npts[j];
+    }
+    if (first < 0 || count < 0 || static_cast<double>(first) + static_cast<double>(count) > total)
+        return fail(VAE21_ERR_ARG, "point range [%lld, %lld) outside the grid", (long long)first, (long long)(first + count));
+    if (first + count > (1ll << 32)) return fail(VAE21_ERR_ARG, "grid indices of one call must stay below 2^32 (shard the grid)");
+    if (int rc = use_device(h)) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int NO = h->dims[h->n_layers];
+    const bool want_best = best_val || best_idx;
+    CK(cudaMemcpyAsync(h->d_obs, obs, sizeof(float) * NO, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_isig, inv_sigma, sizeof(float) * NO, cudaMemcpyHostToDevice, st));
+    if (want_best) CK(cudaMemsetAsync(h->d_key, 0xff, sizeof(unsigned long long), st));
+    LaunchArgs a{};
+    a.in = h->d_obs;  // unused in IN_GRID mode (must be non-null)
+    a.mu = h->d_mu;
+    a.obs = h->d_obs;
+    a.isig = h->d_isig;
+    a.chi2 = chi2_dev;
+    a.argmin_key = want_best ? h->d_key : nullptr;
+    a.in_mode = IN_GRID;
+    a.out_mode = OUT_CHI2;
+    a.n = count;
+    a.row_base = first;
+    for (int j = 0; j < n_dim; ++j) {
+        a.grid_n[j] = npts[j];
+        a.grid_lo[j] = static_cast<float>(x_lo[j]);
+        a.grid_step[j] = npts[j] > 1 ? static_cast<float>((x_hi[j] - x_lo[j]) / (npts[j] - 1)) : 0.f;
+    }
+    if (count > 0)
+        if (int rc = launch(h, a, precision, st)) return rc;
+    if (want_best) {
+        unsigned long long key = ~0ull;
+        CK(cudaMemcpyAsync(&key, h->d_key, sizeof key, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint32_t bits = static_cast<uint32_t>(key >> 32);
+        float v;
+        memcpy(&v, &bits, 4);
+        const bool none = (key == ~0ull) || std::isnan(v);
+        if (best_val) *best_val = none ? NAN : v;
+        if (best_idx) *best_idx = none ? -1 : static_cast<int64_t>(key & 0xffffffffull);
+    }
+    return 0;
+}
+
 int vae21_get_info(vae21_handle* h, int64_t* kernel_launches, float* last_kernel_ms, int* tc_supported) {
     if (!h) return fail(VAE21_ERR_ARG, "null handle");
     if (kernel_launches) *kernel_launches = h->launches;

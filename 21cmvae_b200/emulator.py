@@ -407,6 +407,30 @@ class DirectEmulator:
             return c, bv, bi
         return c
 
+    def chi2_grid(self, points_per_dim, observed, sigma, first=0, count=None, precision=None, out=None):
+        """chi^2 of ``observed`` over a regular grid spanning the training range of every parameter (the [-1, 1] box of
+        ``preprocess.par_transform``: log-spaced in fstar, Vc, fx, linear in the others), generated on the GPU -- a 1e8-point
+        grid never exists in memory.  Returns (best chi^2, flat grid index, the physical parameters of that point).  Shard large
+        grids with ``first`` / ``count``.  Not in the reference."""
+        h = self._handle()
+        nd = len(self.stats.par_min)
+        npts = [int(v) for v in (points_per_dim if np.ndim(points_per_dim) else [points_per_dim] * nd)]
+        nout = len(self.stats.sig_mean)
+        isig = 1.0 / np.broadcast_to(np.asarray(sigma, dtype=np.float64), (nout,))
+        bv, bi = h.chi2_grid(npts, np.asarray(observed, np.float32), isig.astype(np.float32), first=first, count=count, out=out,
+                             precision=_resolve_precision(precision if precision is not None else self.precision))
+        return bv, bi, (self.grid_point(npts, bi) if bi >= 0 else None)
+
+    def grid_point(self, points_per_dim, index):
+        """Physical parameters of point ``index`` of the grid of ``chi2_grid`` (inverse of par_transform on the grid node)."""
+        nd = len(self.stats.par_min)
+        npts = [int(v) for v in (points_per_dim if np.ndim(points_per_dim) else [points_per_dim] * nd)]
+        idx = np.unravel_index(int(index), npts)
+        frac = np.array([i / (n - 1) if n > 1 else 0.0 for i, n in zip(idx, npts)])
+        lo, hi = np.asarray(self.stats.par_min, np.float64), np.asarray(self.stats.par_max, np.float64)
+        t = lo + frac * (hi - lo)
+        return np.array([10.0 ** v if j in pp.LOG_COLUMNS else v for j, v in enumerate(t)])
+
     def test_error(self, relative=True, flow=None, fhigh=None):
         """Error of the emulator for each signal in the test set (emulator.py:409-439)."""
         if self.par_test is None or self.signal_test is None:

@@ -116,6 +116,17 @@ int vae21_chi2(vae21_handle* h, const void* params, int params_dtype, int params
                const float* obs, const float* inv_sigma, float* chi2, int chi2_on_device, float* best_val,
                int64_t* best_idx, int precision, void* stream);
 
+/*
+ * Fused likelihood over a REGULAR GRID generated on the device (BASELINE config 3: 1e8-point grids are never materialised):
+ * point i (C order, last dimension fastest) has NORMALISED coordinates x_j = x_lo[j] + i_j (x_hi[j] - x_lo[j]) / (npts[j] - 1)
+ * -- the [-1, 1] box is the training range of preprocess.par_transform (preprocess.py:105-108).  Evaluates points
+ * [first, first + count) (first + count < 2^32 per call; shard larger grids), writes chi2_dev[i - first] (DEVICE pointer, may be
+ * NULL) and returns the minimum and its global grid index.  obs / inv_sigma: host pointers as in vae21_chi2.
+ */
+int vae21_chi2_grid(vae21_handle* h, int n_dim, const int* npts, const double* x_lo, const double* x_hi, int64_t first, int64_t count,
+                    const float* obs, const float* inv_sigma, float* chi2_dev, float* best_val, int64_t* best_idx, int precision,
+                    void* stream);
+
 /* Pinned host memory from the library's caching pool (for PCIe-rate copies). */
 void* vae21_host_alloc(size_t bytes);
 void vae21_host_free(void* p);

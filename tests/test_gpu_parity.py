@@ -335,3 +335,40 @@ def test_time_predict_and_pinned_pool(rm, direct_fixture, emu_direct):
     gc.collect()
     b = L.pinned_empty((1000, 451), np.float32)  # same size class: the pool hands the block back
     assert b.ctypes.data == addr
+
+
+# ---- device-generated grid (BASELINE config 3) ------------------------------------------------------
+@pytest.mark.parametrize("prec", ["fp32", "fp16e4m3"])
+def test_chi2_grid_matches_explicit_grid(rm, direct_fixture, emu_direct, prec):
+    """chi2_grid generates the grid nodes inside the kernel; the same nodes passed as explicit parameter rows must give the
+    same chi^2 (the explicit path takes log10 of 10**t, so agreement is to rounding, not bitwise), in the reference's C order."""
+    if prec != "fp32":
+        tc_or_skip(emu_direct)
+    npts = [3, 2, 4, 3, 2, 3, 5]
+    total = int(np.prod(npts))
+    f = direct_fixture
+    axes = [np.linspace(f["pmin"][j], f["pmax"][j], n) for j, n in enumerate(npts)]
+    mesh = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(total, 7)
+    params = mesh.copy()
+    params[:, :3] = 10.0 ** params[:, :3]
+    truth = _oracle(rm, f, params[1234 % total])
+    obs = (truth + np.random.default_rng(5).normal(size=451) * 3).astype(np.float32)
+    want, _, _ = emu_direct.chi2(params, obs, 25.0, precision=prec, return_argmin=True)
+    import torch
+
+    out = torch.empty(total, dtype=torch.float32, device="cuda")
+    bv, bi, bp = emu_direct.chi2_grid(npts, obs, 25.0, precision=prec, out=out)
+    got = out.cpu().numpy()
+    assert np.allclose(got, want, rtol=2e-3, atol=1e-4)
+    assert bi == int(np.argmin(got)) and bv == pytest.approx(float(got[bi]))
+    assert np.allclose(bp, params[bi], rtol=1e-12)
+    # a shard of the grid: same values, global index
+    lo, cnt = 301, 500
+    out2 = torch.empty(cnt, dtype=torch.float32, device="cuda")
+    bv2, bi2, _ = emu_direct.chi2_grid(npts, obs, 25.0, first=lo, count=cnt, precision=prec, out=out2)
+    got2 = out2.cpu().numpy()
+    if prec == "fp32":
+        assert np.array_equal(got2, got[lo:lo + cnt])
+    else:  # two MMA-issuing warps: sums are reproducible to ~1e-7 relative, not bitwise (DESIGN.md 3.2)
+        assert np.allclose(got2, got[lo:lo + cnt], rtol=1e-5, atol=0)
+    assert bi2 == lo + int(np.argmin(got2))

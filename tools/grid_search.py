@@ -44,41 +44,32 @@ truth_p = np.array([0.0003, 4.2, 1e-3, 0.055, 1.0, 0.1, 10.0])
 obs = (rm.predict(truth_p, ks, bs, relu, pmin, pmax, mu, sd) + np.random.default_rng(7).normal(size=451) * 25).astype(np.float32)
 isig = np.full(451, 1 / 25.0, np.float32)
 
-# grid axes in the transformed (log10 for the first three) prior box
-axes = [torch.linspace(float(pmin[j]), float(pmax[j]), npd, dtype=torch.float64, device="cuda") for j in range(7)]
+# the grid spans the prior box: nodes are generated inside the kernel prologue (IN_GRID), nothing is materialised
 total = npd**7
 lo, hi = mg.shard_bounds(total, world, rank)
-chunk = 8_000_000
-
-
-def rows_to_params(first, count):
-    idx = torch.arange(first, first + count, device="cuda", dtype=torch.int64)
-    cols = []
-    for j in range(6, -1, -1):
-        cols.append(axes[j][idx % npd])
-        idx = idx // npd
-    p = torch.stack(cols[::-1], dim=1)
-    p[:, :3] = torch.pow(10.0, p[:, :3])
-    return p.contiguous()
-
-
-torch.cuda.synchronize()
+sub = 1 << 30  # points per call (grid indices of one call stay below 2^32)
+best = (float("inf"), -1)
 if world > 1:
     dist.barrier()
-t0 = time.perf_counter()
-best_v, best_i = float("inf"), -1
-for first in range(lo, hi, chunk):
-    n = min(chunk, hi - first)
-    p = rows_to_params(first, n)
-    _, v, i = h.chi2(p, obs, isig, want_chi2=False, want_best=True, precision=L.PRECISIONS[prec])
-    if i >= 0 and v < best_v:
-        best_v, best_i = v, first - lo + i
-gv, gi = mg.global_argmin(best_v, best_i, lo)
 torch.cuda.synchronize()
-dt = time.perf_counter() - t0
+t0 = time.perf_counter()
+pos = lo
+while pos < hi:
+    cnt = min(sub, hi - pos)
+    bv, bi, _ = emu.chi2_grid(npd, obs, 25.0, first=pos, count=cnt, precision=prec)
+    if bi >= 0 and bv < best[0]:
+        best = (bv, bi)
+    pos += cnt
+gv, gi = mg.global_argmin(best[0], best[1], 0) if world > 1 else best
+torch.cuda.synchronize()
+secs = time.perf_counter() - t0
+if world > 1:
+    t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs = float(t.item())
 if rank == 0:
-    print(json.dumps({"grid_points": total, "points_per_dim": npd, "n_gpus": world, "precision": prec, "seconds": dt,
-                      "points_per_s": total / dt, "chi2_min": gv, "argmin_row": gi,
-                      "argmin_params": rows_to_params(gi, 1)[0].tolist(), "truth_params": truth_p.tolist()}))
+    print(json.dumps({"grid_points": total, "points_per_dim": npd, "n_gpus": world, "precision": prec, "seconds": secs,
+                      "points_per_s": total / secs, "chi2_min": gv, "argmin_index": int(gi),
+                      "argmin_params": [float(v) for v in emu.grid_point(npd, gi)], "truth_params": truth_p.tolist()}))
 if world > 1:
     dist.destroy_process_group()
