@@ -211,7 +211,6 @@ def emit(line: dict):
 
 
 def main():
-    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -231,6 +230,7 @@ def main():
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                                    f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
                                    os.environ.get("MASTER_PORT", "29533"), os.path.abspath(__file__)] + sys.argv[1:])
+    _claim_stdout()  # after the self-exec into torchrun: the workers must inherit the caller's fd 1
 
     import torch
     import torch.distributed as dist
@@ -247,7 +247,8 @@ def main():
     kh = importlib.import_module("21cmvae_b200.keras_h5")
     L = importlib.import_module("21cmvae_b200._lib")
     mg = importlib.import_module("21cmvae_b200.multigpu")
-    numa_cores = mg.bind_host_to_gpu(local) if world > 1 else None  # keep pinned buffers on the GPU's NUMA node
+    # keep pinned buffers on the GPU's NUMA node (VAE21_NO_NUMA_BIND=1 disables, for A/B runs)
+    numa_cores = mg.bind_host_to_gpu(local) if (world > 1 and not os.environ.get("VAE21_NO_NUMA_BIND")) else None
 
     rm, ks, bs, relu, mu, sd, pmin, pmax, params = build_problem(args.rows, 20220322 + rank)
     emu = emu_mod.DirectEmulator(stats=pp.NormStats(pmin, pmax, mu, sd), device=local)
@@ -321,10 +322,13 @@ def main():
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - w0) / e2e_steps
     checksum = float(res[:: max(1, n // 1000)].sum())
+    e2e_ranks = None
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        e2e_ranks = [float(x.item()) for x in allt]
+        e2e_s = max(e2e_ranks)
     e2e_val = world * n / e2e_s
 
     if rank == 0:
@@ -371,7 +375,7 @@ def main():
                        "weights": "random-init (Glorot), shipped emulator.h5 absent from the reference checkout",
                        "l2": "working set 1.86 GB/step >> 126 MB L2 (no flush needed)", "parallelism": f"rows sharded x{world}", "host_cores_bound": (len(numa_cores) if numa_cores else None)},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * 56, "d2h_bytes_per_step": n * 1804,
-                    "steps": e2e_steps, "checksum": checksum},
+                    "steps": e2e_steps, "checksum": checksum, "seconds_per_step_by_rank": e2e_ranks},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "check": {"max_abs_err_mK": max_mk, "max_err_over_amplitude": rel, "rows_checked": int(len(idx))},
         }
