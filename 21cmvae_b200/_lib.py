@@ -29,7 +29,7 @@ EXPORTS = [
     "vae21_set_model", "vae21_set_norm", "vae21_predict", "vae21_forward_normalised", "vae21_chi2", "vae21_chi2_grid",
     "vae21_host_alloc", "vae21_host_free", "vae21_host_trim", "vae21_get_info", "vae21_time_predict",
     "vae21_trainer_create", "vae21_trainer_destroy", "vae21_trainer_num_params", "vae21_trainer_set_params",
-    "vae21_trainer_get_params", "vae21_trainer_forward_backward", "vae21_trainer_adam", "vae21_trainer_launches",
+    "vae21_trainer_get_params", "vae21_trainer_forward_backward", "vae21_trainer_adam", "vae21_trainer_epoch", "vae21_trainer_launches",
 ]
 
 
@@ -83,6 +83,7 @@ def load() -> C.CDLL:
         lib.vae21_trainer_get_params.argtypes = [vp, f32p]
         lib.vae21_trainer_forward_backward.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, vp, vp, vp]
         lib.vae21_trainer_adam.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp]
+        lib.vae21_trainer_epoch.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float, i64, vp, vp]
         lib.vae21_trainer_launches.argtypes = [vp, C.POINTER(i64)]
         for name in EXPORTS:
             fn = getattr(lib, name)
@@ -389,6 +390,14 @@ class Trainer:
     def adam(self, grad, lr_t, beta1=0.9, beta2=0.999, eps=1e-7, stream=None):
         _check(self._lib.vae21_trainer_adam(self._t, self._dev_ptr(grad, np.float32, "grad"), float(lr_t), float(beta1),
                                             float(beta2), float(eps), C.c_void_p(int(stream)) if stream else None))
+
+    def epoch(self, x_all, y_all, w_all, perm, n, batch, lr, beta1, beta2, eps, iterations_before, loss_sum, stream=None):
+        """All batches of one epoch in one library call (single GPU); see vae21_trainer_epoch."""
+        _check(self._lib.vae21_trainer_epoch(
+            self._t, self._dev_ptr(x_all, np.float32, "x_all"), self._dev_ptr(y_all, np.float32, "y_all"),
+            self._dev_ptr(w_all, np.float32, "w_all"), self._dev_ptr(perm, np.int32, "perm"), int(n), int(batch), float(lr),
+            float(beta1), float(beta2), float(eps), int(iterations_before), self._dev_ptr(loss_sum, np.float32, "loss_sum"),
+            C.c_void_p(int(stream)) if stream else None))
 
     def launches(self) -> int:
         n = C.c_int64(0)

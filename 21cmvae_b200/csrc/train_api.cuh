@@ -16,6 +16,8 @@ struct vae21_trainer {
     float* act[VAE21_MAX_LAYERS + 1] = {nullptr};                             // act[0] = batch inputs, act[l+1] = output of layer l
     float* delta[2] = {nullptr, nullptr};                                     // ping-pong dL/d(pre-activation... post-mask) buffers
     float *yb = nullptr, *wb = nullptr, *loss_rows = nullptr;
+    float* grad = nullptr;  // [n_params], used by vae21_trainer_epoch (single-GPU fast path)
+    cudaEvent_t throttle[2] = {nullptr, nullptr};
     long long launches = 0;
 };
 
@@ -28,8 +30,7 @@ int trainer_use(vae21_trainer* t) {
 void trainer_forward(vae21_trainer* t, int batch, cudaStream_t st) {
     for (int l = 0; l < t->n_layers; ++l) {
         const int K = t->dims[l], N = t->dims[l + 1];
-        trk::sgemm_kernel<0><<<trk::grid_for(batch, N), 256, 0, st>>>(batch, N, K, t->act[l], K, t->p + t->w_off[l], N, t->act[l + 1], N,
-                                                                      t->p + t->b_off[l], t->relu[l], nullptr, 0);
+        trk::sgemm<0>(batch, N, K, t->act[l], K, t->p + t->w_off[l], N, t->act[l + 1], N, t->p + t->b_off[l], t->relu[l], nullptr, 0, st);
         t->launches++;
     }
 }
@@ -72,6 +73,8 @@ int vae21_trainer_create(int device, int n_layers, const int* dims, const int* r
     CK(cudaMalloc(&t->yb, sizeof(float) * static_cast<size_t>(max_batch) * dims[n_layers]));
     CK(cudaMalloc(&t->wb, sizeof(float) * max_batch));
     CK(cudaMalloc(&t->loss_rows, sizeof(float) * max_batch));
+    CK(cudaMalloc(&t->grad, sizeof(float) * off));
+    for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&t->throttle[i], cudaEventDisableTiming));
     *out = t;
     return 0;
 }
@@ -80,10 +83,12 @@ int vae21_trainer_destroy(vae21_trainer* t) {
     if (!t) return 0;
     cudaSetDevice(t->device);
     cudaDeviceSynchronize();
-    for (float* q : {t->p, t->m, t->v, t->delta[0], t->delta[1], t->yb, t->wb, t->loss_rows})
+    for (float* q : {t->p, t->m, t->v, t->delta[0], t->delta[1], t->yb, t->wb, t->loss_rows, t->grad})
         if (q) cudaFree(q);
     for (int l = 0; l <= t->n_layers; ++l)
         if (t->act[l]) cudaFree(t->act[l]);
+    for (int i = 0; i < 2; ++i)
+        if (t->throttle[i]) cudaEventDestroy(t->throttle[i]);
     delete t;
     return 0;
 }
@@ -130,13 +135,12 @@ int vae21_trainer_forward_backward(vae21_trainer* t, const float* x_all, const f
         for (int l = L - 1; l >= 0; --l) {
             const int K = t->dims[l], N = t->dims[l + 1];
             trk::colsum_kernel<<<(N + 127) / 128, 128, 0, st>>>(d_cur, batch, N, grad + t->b_off[l]);
-            trk::sgemm_kernel<2><<<trk::grid_for(K, N), 256, 0, st>>>(K, N, batch, t->act[l], K, d_cur, N, grad + t->w_off[l], N, nullptr, 0, nullptr, 0);
+            trk::sgemm<2>(K, N, batch, t->act[l], K, d_cur, N, grad + t->w_off[l], N, nullptr, 0, nullptr, 0, st);
             t->launches += 2;
             if (l > 0) {
                 float* d_next = (d_cur == t->delta[0]) ? t->delta[1] : t->delta[0];
                 // dL/d(pre-activation of layer l-1) = (D W_l^T) masked by the ReLU of layer l-1 (its output is act[l])
-                trk::sgemm_kernel<1><<<trk::grid_for(batch, K), 256, 0, st>>>(batch, K, N, d_cur, N, t->p + t->w_off[l], N, d_next, K, nullptr, 0,
-                                                                              t->relu[l - 1] ? t->act[l] : nullptr, K);
+                trk::sgemm<1>(batch, K, N, d_cur, N, t->p + t->w_off[l], N, d_next, K, nullptr, 0, t->relu[l - 1] ? t->act[l] : nullptr, K, st);
                 t->launches++;
                 d_cur = d_next;
             }
@@ -154,6 +158,35 @@ int vae21_trainer_adam(vae21_trainer* t, const float* grad, float lr_t, float be
                                                                                                             beta2, eps);
     t->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+int vae21_trainer_epoch(vae21_trainer* t, const float* x_all, const float* y_all, const float* w_all, const int* perm, int64_t n, int batch,
+                        float lr, float beta1, float beta2, float eps, int64_t iterations_before, float* loss_sum, void* stream) {
+    if (!t) return fail(VAE21_ERR_ARG, "null trainer");
+    if (n < 0 || batch < 1 || batch > t->max_batch) return fail(VAE21_ERR_ARG, "bad n / batch");
+    const int NO = t->dims[t->n_layers];
+    int64_t it = iterations_before;
+    // Keep at most ~2 x 16 steps (< 800 launches) in flight: past the driver's launch-queue depth every further launch blocks
+    // in a slow path (measured: 3.2 ms per step instead of 0.15 ms when a whole epoch of 2,500 launches is queued at once).
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int blk = 0, recorded[2] = {0, 0};
+    for (int64_t lo = 0, step = 0; lo < n; lo += batch, ++step) {
+        if (step > 0 && step % 16 == 0) {
+            CK(cudaEventRecord(t->throttle[blk], st));
+            recorded[blk] = 1;
+            blk ^= 1;
+            if (recorded[blk]) CK(cudaEventSynchronize(t->throttle[blk]));
+        }
+        const int b = static_cast<int>(std::min<int64_t>(batch, n - lo));
+        if (int rc = vae21_trainer_forward_backward(t, x_all, y_all, w_all, perm ? perm + lo : nullptr, lo, b, static_cast<float>(1.0 / (static_cast<double>(NO) * b)),
+                                                    t->grad, loss_sum, stream))
+            return rc;
+        ++it;
+        const double lr_t = static_cast<double>(lr) * std::sqrt(1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(it))) /
+                            (1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(it)));
+        if (int rc = vae21_trainer_adam(t, t->grad, static_cast<float>(lr_t), beta1, beta2, eps, stream)) return rc;
+    }
     return 0;
 }
 

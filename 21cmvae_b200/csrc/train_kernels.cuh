@@ -17,20 +17,23 @@
 
 namespace trk {
 
-constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;  // 256 threads, 4x4 outputs each
+constexpr int BK = 16, NT = 256;  // k-depth of a staged tile, threads per block
 
-// C[M,N] = op(A) op(B) with fused epilogues.
+// C[M,N] = op(A) op(B) with fused epilogues; BM x BN output tile per block, TM x TN outputs per thread ((BM/TM) (BN/TN) = 256).
+// The batch is only 256 rows, so parallelism has to come from many small tiles: 32 x 32 tiles put 88..120 blocks on the 148 SMs
+// for the layer shapes of the emulator where 64 x 64 tiles would put 24..30.
 //   MODE 0 (forward)      A = H [M,K] row-major, B = W [K,N] row-major;  C = A B + bias[n], ReLU if relu
 //   MODE 1 (backward data) A = D [M,K'] row-major (K' = reduction = layer outputs), B = W [N,K'] row-major (used transposed);
 //                          C[m,n] = sum_k D[m,k] W[n,k], multiplied by [mask[m,n] > 0] when mask != nullptr
 //   MODE 2 (backward weight) A = H [K',M] (used transposed: reduction over the batch K'), B = D [K',N];  C[m,n] = sum_k H[k,m] D[k,n]
-template <int MODE>
-__global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B,
-                                                    int ldb, float* __restrict__ C, int ldc, const float* __restrict__ bias, int relu,
-                                                    const float* __restrict__ mask, int ldm) {
+template <int MODE, int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(NT) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B,
+                                                   int ldb, float* __restrict__ C, int ldc, const float* __restrict__ bias, int relu,
+                                                   const float* __restrict__ mask, int ldm) {
+    static_assert((BM / TM) * (BN / TN) == NT, "tile / thread shape");
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, tx = tid % (BN / TN), ty = tid / (BN / TN);
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     float acc[TM][TN];
 #pragma unroll
@@ -38,29 +41,24 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
     for (int k0 = 0; k0 < K; k0 += BK) {
-        // stage the two tiles k-major; each thread loads 4 + 4 elements
+        // stage the two tiles k-major
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int idx = tid + 256 * e;  // 0 .. 1023
-            if (MODE == 2) {
-                // A element (m, k) = H[k][m]: consecutive threads walk m (contiguous in memory)
-                const int mm = idx & 63, kk = idx >> 6;
-                const int m = m0 + mm, k = k0 + kk;
+        for (int e = tid; e < BM * BK; e += NT) {
+            if (MODE == 2) {  // A element (m, k) = H[k][m]: consecutive threads walk m (contiguous in memory)
+                const int mm = e % BM, kk = e / BM, m = m0 + mm, k = k0 + kk;
                 As[kk][mm] = (m < M && k < K) ? A[static_cast<size_t>(k) * lda + m] : 0.f;
-            } else {
-                // A element (m, k) = A[m][k]: consecutive threads walk k
-                const int kk = idx & 15, mm = idx >> 4;
-                const int m = m0 + mm, k = k0 + kk;
+            } else {          // A element (m, k) = A[m][k]: consecutive threads walk k
+                const int kk = e % BK, mm = e / BK, m = m0 + mm, k = k0 + kk;
                 As[kk][mm] = (m < M && k < K) ? A[static_cast<size_t>(m) * lda + k] : 0.f;
             }
-            if (MODE == 1) {
-                // B element (k, n) = W[n][k]
-                const int kk = idx & 15, nn = idx >> 4;
-                const int n = n0 + nn, k = k0 + kk;
+        }
+#pragma unroll
+        for (int e = tid; e < BN * BK; e += NT) {
+            if (MODE == 1) {  // B element (k, n) = W[n][k]
+                const int kk = e % BK, nn = e / BK, n = n0 + nn, k = k0 + kk;
                 Bs[kk][nn] = (n < N && k < K) ? B[static_cast<size_t>(n) * ldb + k] : 0.f;
             } else {
-                const int nn = idx & 63, kk = idx >> 6;
-                const int n = n0 + nn, k = k0 + kk;
+                const int nn = e % BN, kk = e / BN, n = n0 + nn, k = k0 + kk;
                 Bs[kk][nn] = (n < N && k < K) ? B[static_cast<size_t>(k) * ldb + n] : 0.f;
             }
         }
@@ -95,6 +93,18 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
             if (MODE == 1 && mask) v = mask[static_cast<size_t>(m) * ldm + n] > 0.f ? v : 0.f;
             C[static_cast<size_t>(m) * ldc + n] = v;
         }
+    }
+}
+
+// 32 x 32 tiles unless the problem is large enough to fill the GPU with 64 x 64 ones
+template <int MODE>
+inline void sgemm(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias, int relu,
+                  const float* mask, int ldm, cudaStream_t st) {
+    const long long big_blocks = static_cast<long long>((M + 63) / 64) * ((N + 63) / 64);
+    if (big_blocks >= 296) {
+        sgemm_kernel<MODE, 64, 64, 4, 4><<<dim3((N + 63) / 64, (M + 63) / 64), NT, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldm);
+    } else {
+        sgemm_kernel<MODE, 32, 32, 2, 2><<<dim3((N + 31) / 32, (M + 31) / 32), NT, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldm);
     }
 }
 
@@ -157,7 +167,5 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ m, float*
     v[i] = vi;
     p[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
-
-inline dim3 grid_for(int M, int N) { return dim3((N + BN - 1) / BN, (M + BM - 1) / BM); }
 
 }  // namespace trk

@@ -178,7 +178,12 @@ def fit(dims: Sequence[int], relu: Sequence[int], flat_params: np.ndarray, x, y,
             perm = pt.cpu().numpy()
         d_perm = torch.as_tensor(perm.astype(np.int32), device=dev)
         loss_acc.zero_()
-        for lo in range(0, n, batch_size):
+        if world == 1:
+            # one GPU: the whole epoch in one library call (no Python between batches)
+            tr.epoch(dx, dy, dw, d_perm, n, batch_size, optimizer.learning_rate, optimizer.beta_1, optimizer.beta_2, optimizer.epsilon,
+                     optimizer.iterations, loss_acc, stream=stream)
+            optimizer.iterations += (n + batch_size - 1) // batch_size
+        for lo in (range(0, n, batch_size) if world > 1 else ()):
             hi = min(lo + batch_size, n)
             a, b = shard_batch(lo, hi, world, rank)
             if b > a:

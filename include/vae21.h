@@ -171,6 +171,11 @@ int vae21_trainer_get_params(vae21_trainer* t, float* flat_host);
 int vae21_trainer_forward_backward(vae21_trainer* t, const float* x_all, const float* y_all, const float* w_all, const int* idx,
                                    int64_t first, int batch, float grad_scale, float* grad, float* loss_sum, void* stream);
 int vae21_trainer_adam(vae21_trainer* t, const float* grad, float lr_t, float beta1, float beta2, float eps, void* stream);
+/* One epoch on ONE GPU without returning to the host between batches: for every batch of `batch` rows of perm[0..n) (device int32
+ * permutation, NULL = natural order) forward_backward with grad_scale = 1 / (n_out * rows) and adam with update number
+ * iterations_before + 1, + 2, ... (lr_t computed per update as above).  Equivalent to the per-batch calls. */
+int vae21_trainer_epoch(vae21_trainer* t, const float* x_all, const float* y_all, const float* w_all, const int* perm, int64_t n, int batch,
+                        float lr, float beta1, float beta2, float eps, int64_t iterations_before, float* loss_sum, void* stream);
 int vae21_trainer_launches(vae21_trainer* t, int64_t* n);
 
 #ifdef __cplusplus

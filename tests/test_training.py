@@ -264,3 +264,34 @@ def test_direct_emulator_train_end_to_end(rm):
     pred = e.emulator.predict(x.astype(np.float32), precision="fp32")
     want = emu.relative_mse_loss(e.signal_train)(y, pred).mean()
     assert val_loss[-1] == pytest.approx(float(want), rel=1e-3)
+
+
+@pytest.mark.gpu
+def test_epoch_call_equals_per_batch_calls(rm):
+    """vae21_trainer_epoch (all batches in one library call) is the same arithmetic as forward_backward + adam per batch."""
+    L = pkg("_lib")
+    tr = pkg("training")
+    dims, batch, n = (7, 40, 24, 451), 64, 64 * 3 + 17
+    ks, bs, relu, x, y, mos = _problem(dims, n, 33, rm)
+    from oracle import train_ref as tref
+
+    w = tref.sample_weights(y, mos).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    dx, dy, dw = (torch.as_tensor(a).to(dev) for a in (x, y, w))
+    perm = torch.as_tensor(np.random.default_rng(1).permutation(n).astype(np.int32)).to(dev)
+    flat0 = tr.flatten_weights(ks, bs)
+    a, b = L.Trainer(dims, relu, max_batch=batch), L.Trainer(dims, relu, max_batch=batch)
+    a.set_params(flat0)
+    b.set_params(flat0)
+    grad = torch.zeros(a.num_params, dtype=torch.float32, device=dev)
+    la, lb = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+    it, lr = 0, float(np.float32(0.01))  # the epoch call takes the learning rate as a C float
+    for lo in range(0, n, batch):
+        rows = min(batch, n - lo)
+        a.forward_backward(dx, dy, dw, rows, 1.0 / (dims[-1] * rows), grad, la, idx=perm[lo:lo + rows])
+        it += 1
+        b1, b2 = float(np.float32(0.9)), float(np.float32(0.999))  # ... and the betas as C floats
+        a.adam(grad, lr * math.sqrt(1 - b2**it) / (1 - b1**it))
+    b.epoch(dx, dy, dw, perm, n, batch, lr, 0.9, 0.999, 1e-7, 0, lb)
+    assert np.array_equal(a.get_params(), b.get_params())
+    assert float(la.item()) == float(lb.item())
