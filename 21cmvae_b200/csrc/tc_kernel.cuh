@@ -11,8 +11,8 @@
 // comes from the fused parameter transform, the last layer's epilogue applies the output
 // transform (or the chi^2 reduction) and writes coalesced row segments.
 //
-// Warp roles (192 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer (one thread) and
-// TMEM allocator, warps 2..5 = epilogue (thread = tile row = TMEM lane).
+// Warp roles (128 + 128 EPS threads): warp 0 = bulk-copy producer, warps 1 and 2 = MMA issuers (warp 1 also allocates TMEM),
+// warp 3 = prologue (parameter transform -> layer-0 operand, one tile ahead), warps 4.. = epilogue (thread = tile row = TMEM lane).
 //
 // Operand images (validated on hardware by tools/umma_probe.cu):
 //   un-swizzled K-major core-matrix layout [k/8][row][8 x 16-bit]: descriptor LBO = bytes between
@@ -749,7 +749,8 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     auto bar_q_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + NFULL + b); };
     auto bar_act_ready = [&](int j) { return bar0 + 8u * (2 * MAX_SLOTS + NFULL + 2 + j); };  // j < MAX_LCHUNK
     const uint32_t bar_a0_ready = bar0 + 8u * (2 * MAX_SLOTS + NFULL + 2 + MAX_LCHUNK);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + P.off_bar + 8 * (2 * MAX_SLOTS + NFULL + 3 + MAX_LCHUNK));
+    const uint32_t bar_a0_free = bar0 + 8u * (2 * MAX_SLOTS + NFULL + 3 + MAX_LCHUNK);  // layer-0 MMAs of the tile have read a0
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + P.off_bar + 8 * (2 * MAX_SLOTS + NFULL + 4 + MAX_LCHUNK));
     float* s_pmin = reinterpret_cast<float*>(sm + P.off_bar + BAR_BYTES);   // [16] fp32 copies of the prologue constants
     float* s_pscale = s_pmin + 16;                                    // [16] 2 / (pmax - pmin)
     float* s_chi = s_pscale + 16;                                     // [2][EPS-1][128] chi^2 partials of the other column shares
@@ -774,7 +775,8 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         for (int b = 0; b < 2; ++b) mbar_init(bar_q_empty(b), (NEPI / 32) * both + fwd);
         // (chunk_full: one commit from each of the two issuing warps)
         for (int j = 0; j < MAX_LCHUNK; ++j) mbar_init(bar_act_ready(j), (NEPI / 32) * both + fwd);
-        mbar_init(bar_a0_ready, 4 * both + fwd);
+        mbar_init(bar_a0_ready, 1 * both + fwd);  // one arrival from the prologue warp (of each CTA)
+        mbar_init(bar_a0_free, P.issuers);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (tid < 16) {
@@ -1095,6 +1097,10 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                     if (elect_one()) {
                         if (PAIR) mma2_commit_both(bar_chunk_full(seq & (NFULL - 1)));
                         else mma_commit(bar_chunk_full(seq & (NFULL - 1)));
+                        if (C.layer == 0 && C.last_in_layer) {  // the prologue warp(s) may overwrite a0 once these MMAs are done
+                            if (PAIR) mma2_commit_both(bar_a0_free);
+                            else mma_commit(bar_a0_free);
+                        }
                     }
                     __syncwarp();
                 }
@@ -1111,6 +1117,65 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
 #endif
         }
         __syncwarp();
+    } else if (warp == 3) {
+        // ===================== prologue warp: layer-0 operand of every tile ===================
+        // fused parameter transform (preprocess.py:74-78, :105-108) in fp32 -- the operand is split to 16-bit hi/lo pairs
+        // anyway -- -> a0 (k padded to 16).  Runs one tile ahead of the MMAs, off the epilogue warps' critical path
+        // (measured: the same work inside four epilogue warps cost 0.05 ms per 1M rows).
+        const int K0 = P.K0;
+        uint32_t nfree = 0;
+        for (long long unit = unit0; unit < nunits; unit += ustep, ++nfree) {
+            const long long tile = CG * unit + rank;
+            if (nfree > 0) mbar_wait(bar_a0_free, (nfree - 1u) & 1u);
+            for (int rr = 0; rr < MT / 32; ++rr) {
+                const int row = rr * 32 + lane;
+                const long long grow = tile * MT + row;
+                float x[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) x[j] = 0.f;
+                if (DBG & 256) {
+                } else if (grow < a.n && a.in_mode == IN_GRID) {
+                    grid_point(a, static_cast<unsigned long long>(a.row_base + grow), K0, x);
+                } else if (grow < a.n) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j < K0) {
+                            const long long g = grow * K0 + j;
+                            if (a.in_mode == IN_NORMALISED_F32) {
+                                x[j] = reinterpret_cast<const float*>(a.in)[g];
+                            } else {
+                                const double pd = (a.in_mode == IN_PARAMS_F64)
+                                                      ? reinterpret_cast<const double*>(a.in)[g]
+                                                      : static_cast<double>(reinterpret_cast<const float*>(a.in)[g]);
+                                float pf = static_cast<float>(pd);
+                                if (j == nc.floor_col && pd == 0.0) pf = static_cast<float>(nc.floor_val);
+                                float t = pf;
+                                if (nc.log_mask[j]) {
+                                    t = log10f(pf);
+                                    // a finite non-zero double outside the float range: take the slow exact route
+                                    if ((pf == 0.f || isinf(pf)) && pd != 0.0 && !isinf(pd)) t = static_cast<float>(log10(pd));
+                                }
+                                x[j] = fmaf(t - s_pmin[j], s_pscale[j], -1.f);
+                            }
+                        }
+                    }
+                }
+                uint32_t w[16];
+                split16<FMT>(x, w);
+                uint8_t* a0 = sm + P.off_a0;
+                *reinterpret_cast<uint4*>(a0 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(a0 + A_KG_BYTES + row * 16) = make_uint4(w[4], w[5], w[6], w[7]);
+                *reinterpret_cast<uint4*>(a0 + 2 * A_KG_BYTES + row * 16) = make_uint4(w[8], w[9], w[10], w[11]);
+                *reinterpret_cast<uint4*>(a0 + 3 * A_KG_BYTES + row * 16) = make_uint4(w[12], w[13], w[14], w[15]);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if (PAIR && !leader && VAE21_TC_DIRECT_ARRIVE == 1) mbar_arrive_remote(bar_a0_ready, 0);
+                else if (PAIR && !leader && VAE21_TC_DIRECT_ARRIVE == 2) mbar_arrive_remote_release(bar_a0_ready, 0);
+                else mbar_arrive(bar_a0_ready);
+            }
+        }
     } else if (warp >= 4) {
         // ===================== epilogue warps ================================================
         // thread = tile row = TMEM lane; the two warps that share a TMEM sub-partition split the
@@ -1122,7 +1187,6 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         const uint32_t tlane = static_cast<uint32_t>(sub * 32) << 16;
         float* stage = reinterpret_cast<float*>(sm + P.off_stage) + ew * (32 * 20);
         const int NO = P.n_out;
-        const int K0 = P.K0;
         uint32_t seq = 0;
         uint32_t tcount = 0;
 
@@ -1132,52 +1196,6 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             else if (PAIR && !leader && VAE21_TC_DIRECT_ARRIVE == 2) mbar_arrive_remote_release(bar, 0);
             else mbar_arrive(bar);
         };
-        auto write_a0 = [&](long long tile) {
-            // fused parameter transform (preprocess.py:74-78, :105-108) in fp32 -- the operand is
-            // split to 16-bit hi/lo pairs anyway -- -> layer-0 operand (k padded to 16)
-            const long long grow = tile * MT + row;
-            float x[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] = 0.f;
-            if (grow < a.n && a.in_mode == IN_GRID) {
-                grid_point(a, static_cast<unsigned long long>(a.row_base + grow), K0, x);
-            } else if (grow < a.n) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    if (j < K0) {
-                        const long long g = grow * K0 + j;
-                        if (a.in_mode == IN_NORMALISED_F32) {
-                            x[j] = reinterpret_cast<const float*>(a.in)[g];
-                        } else {
-                            const double pd = (a.in_mode == IN_PARAMS_F64)
-                                                  ? reinterpret_cast<const double*>(a.in)[g]
-                                                  : static_cast<double>(reinterpret_cast<const float*>(a.in)[g]);
-                            float pf = static_cast<float>(pd);
-                            if (j == nc.floor_col && pd == 0.0) pf = static_cast<float>(nc.floor_val);
-                            float t = pf;
-                            if (nc.log_mask[j]) {
-                                t = log10f(pf);
-                                // a finite non-zero double outside the float range: take the slow exact route
-                                if ((pf == 0.f || isinf(pf)) && pd != 0.0 && !isinf(pd)) t = static_cast<float>(log10(pd));
-                            }
-                            x[j] = fmaf(t - s_pmin[j], s_pscale[j], -1.f);
-                        }
-                    }
-                }
-            }
-            uint32_t w[16];
-            split16<FMT>(x, w);
-            uint8_t* a0 = sm + P.off_a0;
-            *reinterpret_cast<uint4*>(a0 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4*>(a0 + A_KG_BYTES + row * 16) = make_uint4(w[4], w[5], w[6], w[7]);
-            *reinterpret_cast<uint4*>(a0 + 2 * A_KG_BYTES + row * 16) = make_uint4(w[8], w[9], w[10], w[11]);
-            *reinterpret_cast<uint4*>(a0 + 3 * A_KG_BYTES + row * 16) = make_uint4(w[12], w[13], w[14], w[15]);
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) signal_mma(bar_a0_ready);
-        };
-
-        if (half == 0 && unit0 < nunits) write_a0(CG * unit0 + rank);
 
         for (long long unit = unit0; unit < nunits; unit += ustep, ++tcount) {
             const long long tile = CG * unit + rank;
@@ -1314,11 +1332,6 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 if (lane == 0) {
                     if (C.qbuf >= 0) signal_mma(bar_q_empty(C.qbuf));
                     if (out_dst != DST_FINAL) signal_mma(bar_act_ready(C.idx_in_layer));
-                }
-                const bool last_of_layer = C.last_in_layer != 0;
-                // the layer-0 operand of the NEXT tile can be written as soon as layer 0 of this tile is done
-                if (half == 0 && C.layer == 0 && last_of_layer) {
-                    if (unit + ustep < nunits) write_a0(CG * (unit + ustep) + rank);
                 }
             }
             // tile end: all epilogue warps meet (the output staging tiles alias the activation buffer, and the
