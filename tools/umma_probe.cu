@@ -752,7 +752,7 @@ static int run_f8(int argc, char** argv) {
 // Timing v4: cycles per MMA for kind::f16 (K = 16) vs kind::f8f6f4 (K = 32), one CTA or a CTA pair (cta_group::2, M = 256).
 //   umma_probe u
 // ---------------------------------------------------------------------------------------------
-template <int CG, int KIND, int G>
+template <int CG, int KIND, int G, int MROWS = 128>  // MROWS: accumulator rows per CTA (128, or 64 = half-height MMAs)
 __global__ void __launch_bounds__(128, 1)
 time_kernel4(int N, int a_tmem, int nmma, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -783,7 +783,7 @@ time_kernel4(int N, int a_tmem, int nmma, long long* out) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tm = tmem_base_s;
     if (warp == 0 && rank == 0) {
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((CG * 128) >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((CG * MROWS) >> 4) << 24);
         const uint32_t sA = smem_u32(smem), sB = smem_u32(smem) + 32768;
         const uint32_t b_kg = (uint32_t)(N / CG) * 16;
         const uint64_t da = make_desc(sA, 2048, 128);
@@ -830,10 +830,10 @@ time_kernel4(int N, int a_tmem, int nmma, long long* out) {
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512));
     }
 }
-template <int CG, int KIND>
+template <int CG, int KIND, int MROWS = 128>
 static int run4(int N, int a_tmem, long long* d) {
     const int nmma = 1536;
-    cudaFuncSetAttribute(time_kernel4<CG, KIND, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(time_kernel4<CG, KIND, 6, MROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     for (int rep = 0; rep < 2; ++rep) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(CG);
@@ -846,18 +846,27 @@ static int run4(int N, int a_tmem, long long* d) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        CK(cudaLaunchKernelEx(&cfg, time_kernel4<CG, KIND, 6>, N, a_tmem, nmma, d));
+        CK(cudaLaunchKernelEx(&cfg, time_kernel4<CG, KIND, 6, MROWS>, N, a_tmem, nmma, d));
         CK(cudaDeviceSynchronize());
     }
     long long c = 0;
     CK(cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost));
-    printf("timing4 cta_group=%d kind=%s N=%d a_tmem=%d : %.1f cycles/MMA (N/2 = %d)\n", CG, KIND ? "f8f6f4(K32)" : "f16(K16)", N, a_tmem,
-           (double)c / nmma, N / 2);
+    printf("timing4 cta_group=%d rows/CTA=%d kind=%s N=%d a_tmem=%d : %.1f cycles/MMA (N/2 = %d)\n", CG, MROWS, KIND ? "f8f6f4(K32)" : "f16(K16)", N,
+           a_tmem, (double)c / nmma, N / 2);
     return 0;
 }
-static int run_timing4() {
+static int run_timing4(int half_height) {
     long long* d;
     CK(cudaMalloc(&d, 8));
+    if (half_height) {  // 64 accumulator rows per CTA: does the MMA take half the time?
+        for (int N : {64, 128, 176, 256})
+            for (int at = 0; at < 2; ++at) {
+                run4<1, 0, 64>(N, at, d);
+                run4<2, 0, 64>(N, at, d);
+                run4<1, 1, 64>(N, at, d);
+            }
+        return 0;
+    }
     for (int N : {112, 144, 176, 192, 224, 256})
         for (int at = 0; at < 2; ++at) {
             run4<1, 0>(N, at, d);
@@ -1040,7 +1049,7 @@ int main(int argc, char** argv) {
     if (argv[1][0] == 'c') return run_cluster();
     if (argv[1][0] == 't') return run_timing(argc, argv);
     if (argv[1][0] == 'f') return run_f8(argc, argv);
-    if (argv[1][0] == 'u') return run_timing4();
+    if (argv[1][0] == 'u') return run_timing4(argc > 2 ? atoi(argv[2]) : 0);
     if (argv[1][0] == 's') return run_tma_store(argc, argv);
     if (argv[1][0] == 'p') return run_pingpong();
     const int vi = atoi(argv[1]);
