@@ -26,7 +26,7 @@ PRECISIONS = {"fp32": FP32_SIMT, "fp32_simt": FP32_SIMT, "tc": TC_BF16X3, "bf16x
 
 EXPORTS = [
     "vae21_version", "vae21_last_error", "vae21_device_count", "vae21_create", "vae21_destroy",
-    "vae21_set_model", "vae21_set_norm", "vae21_predict", "vae21_forward_normalised", "vae21_chi2", "vae21_chi2_grid",
+    "vae21_set_model", "vae21_set_norm", "vae21_predict", "vae21_forward_normalised", "vae21_chi2", "vae21_chi2_grid", "vae21_error",
     "vae21_host_alloc", "vae21_host_free", "vae21_host_trim", "vae21_get_info", "vae21_time_predict",
     "vae21_trainer_create", "vae21_trainer_destroy", "vae21_trainer_num_params", "vae21_trainer_set_params",
     "vae21_trainer_get_params", "vae21_trainer_forward_backward", "vae21_trainer_adam", "vae21_trainer_epoch", "vae21_trainer_launches",
@@ -69,6 +69,7 @@ def load() -> C.CDLL:
                                    C.POINTER(i64), i32, vp]
         lib.vae21_chi2_grid.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(C.c_double), C.POINTER(C.c_double), i64, i64, f32p, f32p, vp,
                                         C.POINTER(C.c_float), C.POINTER(i64), i32, vp]
+        lib.vae21_error.argtypes = [vp, vp, i32, i32, i64, vp, i32, f32p, i32, vp, i32, i32, vp]
         lib.vae21_host_alloc.argtypes = [C.c_size_t]
         lib.vae21_host_alloc.restype = vp
         lib.vae21_host_free.argtypes = [vp]
@@ -288,6 +289,29 @@ class Handle:
             isg.ctypes.data_as(C.POINTER(C.c_float)), optr, int(odev), C.byref(bv) if want_best else None,
             C.byref(bi) if want_best else None, int(precision), self._stream_ptr(stream, dev and bool(odev), keep)))
         return out, (bv.value if want_best else None), (bi.value if want_best else None)
+
+    def error(self, params, truth, band_mask=None, relative=True, precision=FP32_SIMT):
+        """Fused emulator.py `error`: per-row rms difference between predict(params) and truth over the bins of `band_mask`
+        (None = all), in % of the row's amplitude in the band (relative) or in mK.  Returns a float32 numpy array (n,)."""
+        if self.dims is None:
+            raise Vae21Error(2, "model not set")
+        ptr, dev, n, dt, keep = self._prep_in(params, self.dims[0])
+        if dt not in (np.float32, np.float64):
+            raise TypeError(f"params dtype {dt} unsupported (float32/float64)")
+        nout = self.dims[-1]
+        tptr, tdev, tshape, tdt, _, tkeep = _unwrap(truth)
+        if tuple(tshape) != (n, nout) or np.dtype(tdt) != np.float32:
+            raise ValueError(f"truth must be float32 with shape ({n}, {nout})")
+        mask = None
+        if band_mask is not None:
+            mask = np.ascontiguousarray(band_mask, dtype=np.float32)
+            if mask.shape != (nout,):
+                raise ValueError(f"band_mask must have shape ({nout},)")
+        out = np.empty(n, np.float32)
+        _check(self._lib.vae21_error(self._h, ptr, F64 if dt == np.float64 else F32, int(dev), n, tptr, int(tdev),
+                                     mask.ctypes.data_as(C.POINTER(C.c_float)) if mask is not None else None, int(bool(relative)),
+                                     out.ctypes.data, 0, int(precision), None))
+        return out
 
     def chi2_grid(self, npts, obs, inv_sigma, x_lo=None, x_hi=None, first=0, count=None, out=None, precision=FP32_SIMT, stream=None):
         """Fused chi^2 over points [first, first + count) of a regular grid in normalised coordinates generated on the device

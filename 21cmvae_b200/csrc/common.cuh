@@ -9,7 +9,7 @@
 // what the kernel reads
 enum : int { IN_PARAMS_F32 = 0, IN_PARAMS_F64 = 1, IN_NORMALISED_F32 = 2, IN_GRID = 3 };
 // what the kernel writes
-enum : int { OUT_PREDICT = 0, OUT_NORMALISED = 1, OUT_CHI2 = 2 };
+enum : int { OUT_PREDICT = 0, OUT_NORMALISED = 1, OUT_CHI2 = 2, OUT_ERROR = 3 };
 
 // Prologue constants: x_j = ((T(p_j) - pmin_j) / prange_j) * 2 - 1 in fp64,
 // T = log10 on masked columns with an exact 0 in `floor_col` replaced by
@@ -32,6 +32,11 @@ struct LaunchArgs {
     const float* isig;   // [Nout] 1/sigma (device), chi2 mode
     float* chi2;         // [n] or nullptr
     unsigned long long* argmin_key;  // packed (float bits << 32 | row) running minimum, or nullptr
+    // OUT_ERROR (emulator.py:129-192): chi2[r] = sqrt(mean_band((pred - truth[r])^2)) [* 100 / max_band |truth[r]| if err_relative];
+    // the band is isig[k] in {0, 1}; err_inv_count = 1 / (number of bins in the band)
+    const float* truth;  // [n, Nout] true signals (device)
+    float err_inv_count;
+    int err_relative;
     long long n;         // rows in this launch
     long long row_base;  // global index of row 0 (for argmin)
     int in_mode;

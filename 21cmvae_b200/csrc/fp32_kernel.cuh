@@ -168,6 +168,42 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
                 }
             }
             if (a.argmin_key && lane == 0 && best != ~0ull) atomicMin(a.argmin_key, best);
+        } else if (a.out_mode == OUT_ERROR) {
+            // fused emulator.py:129-192: rms difference to the row's true signal over the band, optionally in % of its amplitude
+            float part[8], amp[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) part[i] = amp[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int n = col_of(j);
+                if (n < N) {
+                    const float b = __ldg(Bl + n), mu = __ldg(a.mu + n), in_band = __ldg(a.isig + n);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const long long row = rbase + i;
+                        float v = __fadd_rn(acc[i][j], b);
+                        if (L.relu) v = v < 0.f ? 0.f : v;
+                        v = __fadd_rn(__fmul_rn(v, nc.sd), mu);
+                        const float t = row < a.n ? __ldg(a.truth + row * N + n) : 0.f;
+                        const float r = (v - t) * in_band;
+                        part[i] = fmaf(r, r, part[i]);
+                        amp[i] = fmaxf(amp[i], fabsf(t) * in_band);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float s = warp_sum(part[i]);
+                float m = amp[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                const long long row = rbase + i;
+                if (row < a.n && lane == 0) {
+                    float e = sqrtf(s * a.err_inv_count);
+                    if (a.err_relative) e = e / m * 100.f;
+                    a.chi2[row] = e;
+                }
+            }
         } else {
             const bool denorm = (a.out_mode == OUT_PREDICT);
 #pragma unroll

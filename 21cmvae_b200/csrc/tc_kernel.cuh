@@ -301,7 +301,7 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
     P.off_isig = off;
     off += nop * 4;
     P.off_bar = off;
-    off += BAR_BYTES + 2 * 16 * 4 + 2 * (EPS - 1) * 128 * 4;  // barriers + prologue constants + chi^2 partials
+    off += BAR_BYTES + 2 * 16 * 4 + 4 * (EPS - 1) * 128 * 4;  // barriers + prologue constants + chi^2 / amplitude partials
     off = (off + 127) / 128 * 128;
     P.off_ring = off;
     const int avail = SMEM_LIMIT - 128 /*alignment slack*/ - off;
@@ -754,6 +754,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     float* s_pmin = reinterpret_cast<float*>(sm + P.off_bar + BAR_BYTES);   // [16] fp32 copies of the prologue constants
     float* s_pscale = s_pmin + 16;                                    // [16] 2 / (pmax - pmin)
     float* s_chi = s_pscale + 16;                                     // [2][EPS-1][128] chi^2 partials of the other column shares
+    float* s_amp = s_chi + 2 * (EPS - 1) * 128;                       // [2][EPS-1][128] |truth| maxima (OUT_ERROR)
 
     float* s_bias = reinterpret_cast<float*>(sm + P.off_bias);
     float* s_s0 = reinterpret_cast<float*>(sm + P.off_s0);
@@ -796,6 +797,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                     ob = a.obs[n];
                     is = a.isig[n];
                 }
+                if (a.out_mode == OUT_ERROR) is = a.isig[n];  // 1 inside the frequency band, 0 outside
             }
             s_s0[n] = s0;
             s_obs[n] = ob;
@@ -1205,7 +1207,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             // writes two 64-byte row segments
             const int cl = lane & 15, rsel = lane >> 4;
             float* orow = a.out + (tile * MT + sub * 32 + rsel) * static_cast<long long>(NO) + cl;
-            float chi = 0.f;
+            float chi = 0.f, amp = 0.f;
             for (int c = 0; c < n_chunks; ++c) {
                 const Chunk& C = P.C[c];
                 mbar_wait(bar_chunk_full(seq & (NFULL - 1)), (seq / NFULL) & 1u);
@@ -1278,6 +1280,16 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                                 const float rr = (v[i] - s_obs[n + i]) * s_isig[n + i];  // isig = 0 on padding
                                 chi = fmaf(rr, rr, chi);
                             }
+                        } else if (a.out_mode == OUT_ERROR) {
+                            // emulator.py:185-191 fused: squared difference to this row's true signal and its amplitude, in the band
+                            const float* tr = a.truth + grow * static_cast<long long>(NO) + n;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float t = (grow < a.n && n + i < NO) ? __ldg(tr + i) : 0.f;
+                                const float rr = (v[i] - t) * s_isig[n + i];
+                                chi = fmaf(rr, rr, chi);
+                                amp = fmaxf(amp, fabsf(t) * s_isig[n + i]);
+                            }
                         } else if (DBG & 8) {
                             if (v[3] == 12345.f) a.out[0] = v[0];
                         } else {
@@ -1337,8 +1349,22 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             // tile end: all epilogue warps meet (the output staging tiles alias the activation buffer, and the
             // two column halves of a row combine their chi^2 partials here)
             float* chi_buf = s_chi + (tcount & 1u) * (EPS - 1) * 128;
-            if (a.out_mode == OUT_CHI2 && half > 0) chi_buf[(half - 1) * 128 + row] = chi;
+            float* amp_buf = s_amp + (tcount & 1u) * (EPS - 1) * 128;
+            if ((a.out_mode == OUT_CHI2 || a.out_mode == OUT_ERROR) && half > 0) chi_buf[(half - 1) * 128 + row] = chi;
+            if (a.out_mode == OUT_ERROR && half > 0) amp_buf[(half - 1) * 128 + row] = amp;
             asm volatile("bar.sync 1, %0;\n" ::"n"(NEPI) : "memory");
+            if (a.out_mode == OUT_ERROR && half == 0) {
+#pragma unroll
+                for (int hh = 0; hh < EPS - 1; ++hh) {
+                    chi += chi_buf[hh * 128 + row];
+                    amp = fmaxf(amp, amp_buf[hh * 128 + row]);
+                }
+                if (grow < a.n) {
+                    float e = sqrtf(chi * a.err_inv_count);
+                    if (a.err_relative) e = e / amp * 100.f;
+                    a.chi2[grow] = e;
+                }
+            }
             if (a.out_mode == OUT_CHI2 && half == 0) {
 #pragma unroll
                 for (int hh = 0; hh < EPS - 1; ++hh) chi += chi_buf[hh * 128 + row];

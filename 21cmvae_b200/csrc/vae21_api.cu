@@ -570,6 +570,71 @@ int vae21_chi2_grid(vae21_handle* h, int n_dim, const int* npts, const double* x
     return 0;
 }
 
+int vae21_error(vae21_handle* h, const void* params, int params_dtype, int params_on_device, int64_t n, const float* truth,
+                int truth_on_device, const float* band_mask, int relative, float* err, int err_on_device, int precision, void* stream) {
+    if (!h) return fail(VAE21_ERR_ARG, "null handle");
+    if (!h->model_set || !h->norm_set) return fail(VAE21_ERR_STATE, "vae21_set_model / vae21_set_norm have not been called");
+    if (n < 0 || n >= (1ll << 32)) return fail(VAE21_ERR_ARG, "row count must be in [0, 2^32)");
+    if (n == 0) return 0;
+    if (!params || !truth || !err) return fail(VAE21_ERR_ARG, "null pointer");
+    if (params_dtype != VAE21_F32 && params_dtype != VAE21_F64) return fail(VAE21_ERR_ARG, "params_dtype %d", params_dtype);
+    if (int rc = use_device(h)) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int K0 = h->dims[0], NO = h->dims[h->n_layers];
+    const size_t in_elt = params_dtype == VAE21_F64 ? 8 : 4;
+    // band mask (all ones when NULL) travels in the inv_sigma slot
+    std::vector<float> mask(NO, 1.f);
+    int in_band = NO;
+    if (band_mask) {
+        in_band = 0;
+        for (int k = 0; k < NO; ++k) {
+            mask[k] = band_mask[k] != 0.f ? 1.f : 0.f;
+            in_band += mask[k] != 0.f;
+        }
+    }
+    if (in_band == 0) return fail(VAE21_ERR_ARG, "the frequency band contains no bin");
+    CK(cudaMemcpyAsync(h->d_isig, mask.data(), sizeof(float) * NO, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // `mask` goes out of scope
+    void *d_par = nullptr, *d_truth = nullptr, *d_err = nullptr;
+    auto cleanup = [&]() {
+        for (void* p : {d_par, d_truth, d_err})
+            if (p) cudaFree(p);
+    };
+    LaunchArgs a{};
+    a.in = params;
+    a.truth = truth;
+    a.chi2 = err;
+    if (!params_on_device) {
+        if (cudaMalloc(&d_par, n * K0 * in_elt) != cudaSuccess) { cleanup(); return fail(VAE21_ERR_NOMEM, "device allocation failed"); }
+        cudaMemcpyAsync(d_par, params, n * K0 * in_elt, cudaMemcpyHostToDevice, st);
+        a.in = d_par;
+    }
+    if (!truth_on_device) {
+        if (cudaMalloc(&d_truth, sizeof(float) * n * NO) != cudaSuccess) { cleanup(); return fail(VAE21_ERR_NOMEM, "device allocation failed"); }
+        cudaMemcpyAsync(d_truth, truth, sizeof(float) * n * NO, cudaMemcpyHostToDevice, st);
+        a.truth = static_cast<const float*>(d_truth);
+    }
+    if (!err_on_device) {
+        if (cudaMalloc(&d_err, sizeof(float) * n) != cudaSuccess) { cleanup(); return fail(VAE21_ERR_NOMEM, "device allocation failed"); }
+        a.chi2 = static_cast<float*>(d_err);
+    }
+    a.mu = h->d_mu;
+    a.obs = h->d_obs;
+    a.isig = h->d_isig;
+    a.in_mode = params_dtype == VAE21_F64 ? IN_PARAMS_F64 : IN_PARAMS_F32;
+    a.out_mode = OUT_ERROR;
+    a.n = n;
+    a.err_inv_count = 1.f / static_cast<float>(in_band);
+    a.err_relative = relative ? 1 : 0;
+    int rc = launch(h, a, precision, st);
+    if (rc == 0 && !err_on_device) {
+        if (cudaMemcpyAsync(err, d_err, sizeof(float) * n, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = fail(VAE21_ERR_CUDA, "copy back failed");
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == 0) rc = fail(VAE21_ERR_CUDA, "error kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cleanup();
+    return rc;
+}
+
 int vae21_get_info(vae21_handle* h, int64_t* kernel_launches, float* last_kernel_ms, int* tc_supported) {
     if (!h) return fail(VAE21_ERR_ARG, "null handle");
     if (kernel_launches) *kernel_launches = h->launches;

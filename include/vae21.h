@@ -127,6 +127,15 @@ int vae21_chi2_grid(vae21_handle* h, int n_dim, const int* npts, const double* x
                     const float* obs, const float* inv_sigma, float* chi2_dev, float* best_val, int64_t* best_idx, int precision,
                     void* stream);
 
+/*
+ * Fused figure of merit (emulator.py:129-192 `error`, :409-439 `test_error`): err[i] = sqrt(mean_k (predict(params_i)[k] -
+ * truth[i][k])^2) over the bins with band_mask[k] != 0 (NULL = all bins), in mK; with relative != 0 divided by max_k |truth[i][k]|
+ * over the same bins and multiplied by 100 (%).  The 451-bin predictions never leave the GPU.  params / truth / err may each be
+ * host or device pointers; band_mask is a host pointer.  Synchronous.
+ */
+int vae21_error(vae21_handle* h, const void* params, int params_dtype, int params_on_device, int64_t n, const float* truth,
+                int truth_on_device, const float* band_mask, int relative, float* err, int err_on_device, int precision, void* stream);
+
 /* Pinned host memory from the library's caching pool (for PCIe-rate copies). */
 void* vae21_host_alloc(size_t bytes);
 void vae21_host_free(void* p);

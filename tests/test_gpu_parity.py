@@ -372,3 +372,30 @@ def test_chi2_grid_matches_explicit_grid(rm, direct_fixture, emu_direct, prec):
     else:  # two MMA-issuing warps: sums are reproducible to ~1e-7 relative, not bitwise
         assert np.allclose(got2, got[lo:lo + cnt], rtol=1e-5, atol=0)
     assert bi2 == lo + int(np.argmin(got2))
+
+
+# ---- fused figure of merit (emulator.py:129-192, :409-439) -------------------------------------------
+@pytest.mark.parametrize("prec", ["fp32", "fp16e4m3"])
+def test_fused_error_matches_numpy_error(rm, direct_fixture, prec):
+    """DirectEmulator.test_error runs predict + band selection + rms + amplitude in one kernel; it must agree with the
+    reference's numpy `error` applied to the oracle's predictions, for every band variant incl. the (N, 1) quirk."""
+    emu = pkg("emulator")
+    f = direct_fixture
+    par = rm.draw_params(333, seed=41)
+    pred = _oracle(rm, f, par)
+    truth = (pred * (1 + 0.01 * np.random.default_rng(2).normal(size=pred.shape)) + 0.3).astype(np.float32)
+    e = _direct(f)
+    if prec != "fp32":
+        tc_or_skip(e)
+    e.par_test, e.signal_test = par, truth
+    nu = e.frequencies
+    for kw in ({}, {"relative": False}, {"flow": 50.0, "fhigh": 120.0}, {"flow": 80.0}, {"fhigh": 100.0, "relative": False}):
+        want = emu.error(truth, pred.astype(np.float32), nu_arr=nu, **{"relative": True, **kw})
+        got = e.test_error(precision=prec, **kw)
+        assert got.shape == want.shape, kw
+        assert np.allclose(got, want, rtol=2e-4, atol=1e-5), kw
+    # single signal, host float64 truth
+    one = e.error_of(par[0], truth[0].astype(np.float64), precision=prec)
+    assert one.shape == (1,) and np.isclose(one[0], emu.error(truth[0], pred[0].astype(np.float32))[0], rtol=2e-4)
+    with pytest.raises(Exception):
+        e.error_of(par, truth, flow=1e6, precision=prec)  # empty band
