@@ -513,8 +513,12 @@ class AutoEncoderEmulator:
             raise RuntimeError("call load_model() first")
         return self._chain.predict(params, precision=precision if precision is not None else self.precision, out=out)
 
-    def test_error(self, relative=True, flow=None, fhigh=None):
+    def test_error(self, relative=True, flow=None, fhigh=None, precision=None):
+        """emulator.py:797-827, fused on the GPU like DirectEmulator.test_error."""
         if self.par_test is None or self.signal_test is None:
             raise ValueError("no test set was given")
-        return error(self.signal_test, self.predict(self.par_test), relative=relative, nu_arr=self.frequencies,
-                     flow=flow, fhigh=fhigh)
+        if self._chain is None:
+            raise ValueError("call load_model() first")
+        self._chain.frequencies = self.frequencies
+        return self._chain.error_of(self.par_test, self.signal_test, relative=relative, flow=flow, fhigh=fhigh,
+                                    precision=precision if precision is not None else self.precision)
