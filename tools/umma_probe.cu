@@ -1014,6 +1014,120 @@ static int run_pingpong() {
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Layout probe for HALF-HEIGHT pair MMAs (cta_group::2, M = 128: 64 accumulator rows per CTA) -- groundwork for running two
+// half-height tiles per CTA.  A[m][k] = m + 128 k (exact in fp16), B = identity on the first 16 columns, so D[m][n] = A[m][n] names
+// its own (m, n); TMEM is pre-filled with -1.  Prints, per CTA, which accumulator row every TMEM lane holds.
+//   umma_probe h <d_lane_offset: 0 or 64>
+// ---------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+half_height_kernel(float* __restrict__ out /*[2][128][32]*/, int d_lane) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
+    constexpr int K = 16, N = 32;
+    uint16_t* sA = reinterpret_cast<uint16_t*>(smem);           // [K/8][64][8]
+    uint16_t* sB = reinterpret_cast<uint16_t*>(smem + 4096);    // [K/8][N/2][8]: this CTA's rows n = 16 rank .. 16 rank + 15
+    for (int e = tid; e < 64 * K; e += 128) {
+        const int m = e / K, k = e % K;
+        const float v = (float)(64 * (int)rank + m + 128 * k);
+        __half h = __float2half_rn(v);
+        sA[((k >> 3) * 64 + m) * 8 + (k & 7)] = *reinterpret_cast<uint16_t*>(&h);
+    }
+    for (int e = tid; e < (N / 2) * K; e += 128) {
+        const int nl = e / K, k = e % K, n = (N / 2) * (int)rank + nl;
+        __half h = __float2half_rn((n < 16 && n == k) ? 1.f : 0.f);
+        sB[((k >> 3) * (N / 2) + nl) * 8 + (k & 7)] = *reinterpret_cast<uint16_t*>(&h);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tm = tmem_base_s;
+    {   // sentinel fill: every lane, columns 0..31
+        uint32_t r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(-1.f);
+        for (int c = 0; c < N; c += 8) {
+            const uint32_t addr = tm + ((uint32_t)(warp * 32) << 16) + c;
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(addr), "r"(r[0]), "r"(r[1]),
+                         "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    if (rank == 0 && tid == 0) {
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f16 x f16 -> f32, M = 128 over the pair
+        const uint64_t da = make_desc(smem_u32(sA), 64 * 16, 128);
+        const uint64_t db = make_desc(smem_u32(sB), (N / 2) * 16, 128);
+        const uint32_t d = tm + ((uint32_t)d_lane << 16);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d), "l"(da),
+                     "l"(db), "r"(idesc), "r"(0u) : "memory");
+        asm volatile("{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\ttcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}\n" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    mbar_wait(&bar, 0, nullptr, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    for (int c = 0; c < N; c += 8) {
+        uint32_t r[8];
+        const uint32_t addr = tm + ((uint32_t)(warp * 32) << 16) + c;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(addr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[((size_t)rank * 128 + tid) * N + c + i] = __uint_as_float(r[i]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512));
+}
+static int run_half_height(int argc, char** argv) {
+    const int d_lane = argc > 2 ? atoi(argv[2]) : 0;
+    float* d;
+    CK(cudaMalloc(&d, 2 * 128 * 32 * 4));
+    CK(cudaMemset(d, 0, 2 * 128 * 32 * 4));
+    half_height_kernel<<<2, 128, 16 * 1024>>>(d, d_lane);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("half-height probe d_lane=%d: CUDA error %s\n", d_lane, cudaGetErrorString(e)); return 2; }
+    std::vector<float> h(2 * 128 * 32);
+    CK(cudaMemcpy(h.data(), d, h.size() * 4, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < 2; ++r) {
+        printf("CTA %d (d_lane %d): TMEM lane -> accumulator row m held in column 0 (x = untouched), then column -> n for the first written lane\n", r, d_lane);
+        int first = -1;
+        for (int lane = 0; lane < 128; ++lane) {
+            const float v = h[((size_t)r * 128 + lane) * 32 + 0];
+            if (v == -1.f) printf(" x");
+            else { printf(" %d", (int)v % 128); if (first < 0) first = lane; }
+            if (lane % 32 == 31) printf("\n");
+        }
+        if (first >= 0) {
+            printf("  lane %d columns:", first);
+            for (int c = 0; c < 32; ++c) {
+                const float v = h[((size_t)r * 128 + first) * 32 + c];
+                if (v == -1.f) printf(" x"); else printf(" k%d", (int)v / 128);
+            }
+            printf("\n");
+        }
+    }
+    return 0;
+}
+
 static uint16_t to16(float x, int fp16) {
     if (fp16) {
         __half h = __float2half_rn(x);
@@ -1052,6 +1166,7 @@ int main(int argc, char** argv) {
     if (argv[1][0] == 'u') return run_timing4(argc > 2 ? atoi(argv[2]) : 0);
     if (argv[1][0] == 's') return run_tma_store(argc, argv);
     if (argv[1][0] == 'p') return run_pingpong();
+    if (argv[1][0] == 'h') return run_half_height(argc, argv);
     const int vi = atoi(argv[1]);
     if (vi < 0 || vi >= nvar) return 1;
     const Variant v = table[vi];
