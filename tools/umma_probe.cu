@@ -1066,6 +1066,15 @@ half_height_kernel(float* __restrict__ out /*[2][128][32]*/, int d_lane) {
             asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(addr), "r"(r[0]), "r"(r[1]),
                          "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
         }
+        // A operand candidate in TMEM columns 64..71 (k pairs): lane L, column c holds fp16 (L + 128 (2c)) | fp16 (L + 128 (2c + 1)) << 16
+        uint32_t ar[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            __half lo = __float2half_rn((float)(tid + 128 * (2 * c))), hi = __float2half_rn((float)(tid + 128 * (2 * c + 1)));
+            ar[c] = (uint32_t)(*reinterpret_cast<uint16_t*>(&lo)) | ((uint32_t)(*reinterpret_cast<uint16_t*>(&hi)) << 16);
+        }
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(tm + ((uint32_t)(warp * 32) << 16) + 64u),
+                     "r"(ar[0]), "r"(ar[1]), "r"(ar[2]), "r"(ar[3]), "r"(ar[4]), "r"(ar[5]), "r"(ar[6]), "r"(ar[7]) : "memory");
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -1076,7 +1085,11 @@ half_height_kernel(float* __restrict__ out /*[2][128][32]*/, int d_lane) {
         const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f16 x f16 -> f32, M = 128 over the pair
         const uint64_t da = make_desc(smem_u32(sA), 64 * 16, 128);
         const uint64_t db = make_desc(smem_u32(sB), (N / 2) * 16, 128);
-        const uint32_t d = tm + ((uint32_t)d_lane << 16);
+        const uint32_t d = tm + ((uint32_t)(d_lane % 1000) << 16);
+        if (d_lane >= 1000)  // A from TMEM columns 64..71: every lane holds lane + 128 (2 col + half), so D[m][k] names its source
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d),
+                         "r"(tm + 64u), "l"(db), "r"(idesc), "r"(0u) : "memory");
+        else
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d), "l"(da),
                      "l"(db), "r"(idesc), "r"(0u) : "memory");
         asm volatile("{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\ttcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}\n" ::"r"(smem_u32(&bar)) : "memory");
@@ -1113,7 +1126,7 @@ static int run_half_height(int argc, char** argv) {
         for (int lane = 0; lane < 128; ++lane) {
             const float v = h[((size_t)r * 128 + lane) * 32 + 0];
             if (v == -1.f) printf(" x");
-            else { printf(" %d", (int)v % 128); if (first < 0) first = lane; }
+            else { printf(" %d", (int)v % 128); if (first < 0) first = lane; }  // SS: row m; TS: source TMEM lane of A
             if (lane % 32 == 31) printf("\n");
         }
         if (first >= 0) {
