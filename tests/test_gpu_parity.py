@@ -399,3 +399,25 @@ def test_fused_error_matches_numpy_error(rm, direct_fixture, prec):
     assert one.shape == (1,) and np.isclose(one[0], emu.error(truth[0], pred[0].astype(np.float32))[0], rtol=2e-4)
     with pytest.raises(Exception):
         e.error_of(par, truth, flow=1e6, precision=prec)  # empty band
+
+
+# ---- planner generality: other Dense stacks through every tensor-core format --------------------------------
+@pytest.mark.parametrize("dims", [(7, 16, 11), (3, 40, 24, 451), (16, 100, 200, 100, 30), (7, 480, 64), (5, 33, 47, 19, 130, 7)])
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3", "fp16e4m3"])
+def test_tc_paths_on_other_architectures(rm, dims, prec):
+    """The schedule planner is generic over Dense stacks (widths not multiples of 16, narrow outputs, up to 16 inputs); whatever it
+    accepts must meet the tensor-core tolerance in sigma units (0.01 mK rms / 0.05 mK max at 50 mK per sigma)."""
+    emu = pkg("emulator")
+    kh = pkg("keras_h5")
+    ks, bs, relu = rm.glorot_chain(dims, seed=sum(dims))
+    rng = np.random.default_rng(1)
+    bs = [rng.normal(scale=0.1, size=b.shape).astype(np.float32) for b in bs]
+    m = emu.DenseModel(kh.DenseChainWeights(ks, bs, relu, name="generic"))
+    if not m.handle.info()["tc_supported"]:
+        pytest.skip("stack does not fit the tensor-core plan")
+    x = rng.uniform(-1, 1, size=(777, dims[0])).astype(np.float32)
+    want = rm.dense_chain(x, ks, bs, relu)
+    y32 = m.predict(x, precision="fp32")
+    assert _rel_err(y32, want) <= FP32_TOL
+    d = m.predict(x, precision=prec).astype(np.float64) - want
+    assert np.sqrt(np.mean(d * d, axis=1)).max() <= 2e-4 and np.abs(d).max() <= 1e-3
