@@ -1209,16 +1209,20 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             float* orow = a.out + (tile * MT + sub * 32 + rsel) * static_cast<long long>(NO) + cl;
             float chi = 0.f, amp = 0.f;
             for (int c = 0; c < n_chunks; ++c) {
+                // The chunk record is read BEFORE the wait: the (dynamically indexed) constant loads then overlap the wait instead
+                // of sitting, one dependent ~100-cycle load after the other, on the critical path behind it (the wait's inline
+                // assembly is a compiler barrier, so loads placed after it are issued after it).
                 const Chunk& C = P.C[c];
-                mbar_wait(bar_chunk_full(seq & (NFULL - 1)), (seq / NFULL) & 1u);
-                ++seq;
-                tc_fence_after();
-                const float* bl = s_bias + C.bias_n0;
-                const int ng = C.ncols / 16;
-                const uint32_t tbase = tm + tlane + static_cast<uint32_t>(C.dcol);
+                const int c_bias_n0 = C.bias_n0, c_ncols = C.ncols, c_dcol = C.dcol, c_n0 = C.n0, c_qbuf = C.qbuf, c_idx = C.idx_in_layer;
                 const int out_dst = C.out_dst;
                 const bool do_relu = C.relu != 0;
                 const float inv_s8 = (FMT == 2) ? C.inv_s8 : 1.f;
+                mbar_wait(bar_chunk_full(seq & (NFULL - 1)), (seq / NFULL) & 1u);
+                ++seq;
+                tc_fence_after();
+                const float* bl = s_bias + c_bias_n0;
+                const int ng = c_ncols / 16;
+                const uint32_t tbase = tm + tlane + static_cast<uint32_t>(c_dcol);
                 auto process = [&](uint32_t (&r)[16], int g) {
                     const uint32_t taddr = tbase + static_cast<uint32_t>(16 * g);
                     if (out_dst != DST_FINAL) {
@@ -1256,14 +1260,14 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                         } else if (out_dst == DST_TMEM) {
                             tmem_st16(taddr, w);  // in place: these 16 columns become the next layer's k-step
                         } else {
-                            uint8_t* dst = sm + P.off_act + ((C.n0 >> 4) + g) * KSTEP_BYTES + row * 16;
+                            uint8_t* dst = sm + P.off_act + ((c_n0 >> 4) + g) * KSTEP_BYTES + row * 16;
                             *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
                             *reinterpret_cast<uint4*>(dst + A_KG_BYTES) = make_uint4(w[4], w[5], w[6], w[7]);
                             *reinterpret_cast<uint4*>(dst + 2 * A_KG_BYTES) = make_uint4(w[8], w[9], w[10], w[11]);
                             *reinterpret_cast<uint4*>(dst + 3 * A_KG_BYTES) = make_uint4(w[12], w[13], w[14], w[15]);
                         }
                     } else {
-                        const int n = C.n0 + 16 * g;
+                        const int n = c_n0 + 16 * g;
                         const float s1 = ((a.out_mode == OUT_NORMALISED) ? 1.f : nc.sd) * inv_s8;
                         float v[16];
 #pragma unroll
@@ -1342,8 +1346,8 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 tc_fence_before();
                 __syncwarp();  // every lane's writes / reads are done and fenced before the elected lane signals
                 if (lane == 0) {
-                    if (C.qbuf >= 0) signal_mma(bar_q_empty(C.qbuf));
-                    if (out_dst != DST_FINAL) signal_mma(bar_act_ready(C.idx_in_layer));
+                    if (c_qbuf >= 0) signal_mma(bar_q_empty(c_qbuf));
+                    if (out_dst != DST_FINAL) signal_mma(bar_act_ready(c_idx));
                 }
             }
             // tile end: all epilogue warps meet (the output staging tiles alias the activation buffer, and the

@@ -26,7 +26,7 @@ emu.emulator = emu_mod.DenseModel(kh.DenseChainWeights(ks, bs, relu, name="emula
 p = torch.from_numpy(rm.draw_params(rows, seed=1)).cuda()
 o = torch.empty((rows, 451), dtype=torch.float32, device="cuda")
 for _ in range(3):
-    emu.predict(p, out=o, precision="bf16x3")
+    emu.predict(p, out=o, precision=os.environ.get("VAE21_TIMING_PRECISION", "fp16e4m3"))
 torch.cuda.synchronize()
 buf = (C.c_longlong * (160 * 16))()
 lib = L.load()
