@@ -960,16 +960,20 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
 #endif
                     const int nk = min(2 * kps, nst - s);  // k-steps of this iteration (two ring slots' worth)
                     const bool two = (nk > kps);           // second slot in use
-                    // the k-steps of this iteration may cross into the next chunk of the producing layer
-                    if (s + nk - 1 >= next_src_k) {
-                        do {
-                            const int j = src - C.src_first;
-                            { TSTART sync_event(bar_act_ready(j), (act_cnt[j]++) & 1u); TADD(tm_evt[C.layer < 5 ? C.layer : 4]) }
-                            ++src;
-                            next_src_k = (src < src_end) ? (P.C[src].n0 >> 4) : 0x7fffffff;
-                        } while (s + nk - 1 >= next_src_k);
-                        tc_fence_after();
-                    }
+                    // the k-steps of this iteration may cross into the next chunk of the producing layer (both issuers pass these
+                    // waits; the one that issues this iteration does so AFTER its ring-slot waits, which are normally already
+                    // satisfied -- the producer runs ahead -- so that nothing but the MMA issue follows the operand wake-up)
+                    auto wait_operands = [&]() {
+                        if (s + nk - 1 >= next_src_k) {
+                            do {
+                                const int j = src - C.src_first;
+                                { TSTART sync_event(bar_act_ready(j), (act_cnt[j]++) & 1u); TADD(tm_evt[C.layer < 5 ? C.layer : 4]) }
+                                ++src;
+                                next_src_k = (src < src_end) ? (P.C[src].n0 >> 4) : 0x7fffffff;
+                            } while (s + nk - 1 >= next_src_k);
+                            tc_fence_after();
+                        }
+                    };
                     int slot1 = slot + 1;
                     uint32_t ph1 = rphase;
                     if (slot1 == nslots) {
@@ -979,9 +983,11 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                     const uint32_t full0 = bar0 + 8u * slot, full1 = bar0 + 8u * slot1;
                     const bool mine = !two_issuers || ((it & 1) == mw);
                     if (!mine) {
-                        // the other issuing warp handles this iteration
+                        wait_operands();  // the other issuing warp handles this iteration
                     } else if ((DBG & 128) && PAIR && !leader) {
+                        wait_operands();
                     } else if (PAIR && !leader) {
+                        wait_operands();
                         // forwarder: my halves of these stages have landed -> tell the issuer
                         mbar_wait(full0, rphase);
                         if (lane == 0) mbar_arrive_remote(full0, 0);
@@ -1002,6 +1008,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                             }
                             TADD(tm_ring)
                         }
+                        wait_operands();
                         tc_fence_after();
 #if VAE21_TC_TIMING
                         const long long t_issue0 = clock64();
