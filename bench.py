@@ -356,7 +356,7 @@ def main():
         if os.path.isfile(tp):
             roof["traffic"] = json.load(open(tp)).get(prec_name)
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is a rank-0, N = 1 measurement
             threads = len(os.sched_getaffinity(0))
             sample_rows = min(n, 131_072)
             once = make_cpu_port(rm, ks, bs, relu, mu, sd, pmin, pmax, threads)
