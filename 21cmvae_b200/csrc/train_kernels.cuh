@@ -109,11 +109,13 @@ inline void sgemm(int M, int N, int K, const float* A, int lda, const float* B, 
 }
 
 // rows idx[i] (or first + i when idx == nullptr) of the resident set -> contiguous batch buffers
+// (step != nullptr: the kernel runs inside a replayed CUDA graph and takes batch number *step of the permutation `idx`)
 __global__ void gather_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ W, const int* __restrict__ idx,
-                              long long first, int batch, int nx, int ny, float* __restrict__ xb, float* __restrict__ yb, float* __restrict__ wb) {
+                              long long first, int batch, int nx, int ny, float* __restrict__ xb, float* __restrict__ yb, float* __restrict__ wb,
+                              const int* __restrict__ step) {
     const int row = blockIdx.x;
     if (row >= batch) return;
-    const long long src = idx ? idx[row] : first + row;
+    const long long src = step ? idx[static_cast<long long>(*step) * batch + row] : (idx ? idx[row] : first + row);
     for (int j = threadIdx.x; j < ny; j += blockDim.x) yb[static_cast<size_t>(row) * ny + j] = Y[src * ny + j];
     for (int j = threadIdx.x; j < nx; j += blockDim.x) xb[static_cast<size_t>(row) * nx + j] = X[src * nx + j];
     if (threadIdx.x == 0) wb[row] = W[src];
@@ -156,10 +158,12 @@ __global__ void colsum_kernel(const float* __restrict__ D, int M, int N, float* 
 }
 
 // Keras-2.x Adam (non-amsgrad): m = b1 m + (1 - b1) g; v = b2 v + (1 - b2) g^2; p -= lr_t m / (sqrt(v) + eps)
+// (lr_arr != nullptr: replayed graph, the step's learning rate is lr_arr[*step])
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g, long long n,
-                            float lr_t, float b1, float b2, float eps) {
+                            float lr_t, float b1, float b2, float eps, const float* __restrict__ lr_arr, const int* __restrict__ step) {
     const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (i >= n) return;
+    if (lr_arr) lr_t = lr_arr[*step];
     const float gi = g[i];
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
@@ -167,5 +171,8 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ m, float*
     v[i] = vi;
     p[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
+
+__global__ void step_inc_kernel(int* step) { *step += 1; }
+__global__ void add_scalar_kernel(float* dst, const float* src) { dst[0] += src[0]; }
 
 }  // namespace trk
