@@ -162,14 +162,15 @@ int vae21_time_predict(vae21_handle* h, const void* params_dev, int params_dtype
  * ---- training (replaces the Keras `fit` behind DirectEmulator.train, emulator.py:339-381) ---------------
  * A trainer owns the fp32 parameters of a Dense stack in Keras `get_weights()` order (per layer: kernel
  * [in,out] row-major, then bias), the Adam moments, and batch workspaces.  One optimisation step is
- *   forward_backward (gathers the batch rows idx[0..batch) -- or first..first+batch when idx is NULL -- from the
- *   device-resident set, runs forward + relative-MSE loss (emulator.py:51-83: per-sample MSE times w_i = 1/amp_i^2)
- *   + backward; writes the gradient of (sum over the batch of loss_i) * n_out * grad_scale ... i.e. with
- *   grad_scale = 1 / (n_out * global_batch) the gradient of the global-batch mean loss restricted to these rows)
- *   [all-reduce `grad` over the data-parallel ranks here]
- *   adam (Keras semantics; lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) is computed by the caller).
- * loss_sum (device, 1 float) is incremented by sum_i loss_i.  grad == NULL: forward + loss only (validation).
- * All pointers except `out`/`n`/flat_host are DEVICE pointers.
+ *   1. vae21_trainer_forward_backward: gather the batch rows idx[0..batch) (or first..first+batch when idx is NULL) from the
+ *      device-resident set x_all [n, n_in], y_all [n, n_out], w_all [n]; forward; loss_i = w_i * mean_k (y_ik - p_ik)^2 (the
+ *      relative MSE of emulator.py:51-83 with w_i = 1 / amplitude_i^2); backward.  grad [num_params] receives
+ *      d/dparams of grad_scale * n_out * sum_i loss_i: pass grad_scale = 1 / (n_out * rows of the GLOBAL batch) and the sum of
+ *      the ranks' gradients is the gradient of the batch-mean loss Keras minimises.  loss_sum[0] += sum_i loss_i.
+ *      grad == NULL: forward + loss only (validation).
+ *   2. [data parallel: all-reduce (sum) `grad` over the ranks]
+ *   3. vae21_trainer_adam: Keras Adam; the caller passes lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) of update number t.
+ * All pointers except `out` / `n` / flat_host are DEVICE pointers.
  */
 typedef struct vae21_trainer vae21_trainer;
 int vae21_trainer_create(int device, int n_layers, const int* dims, const int* relu_flags, int max_batch, vae21_trainer** out);
@@ -180,9 +181,9 @@ int vae21_trainer_get_params(vae21_trainer* t, float* flat_host);
 int vae21_trainer_forward_backward(vae21_trainer* t, const float* x_all, const float* y_all, const float* w_all, const int* idx,
                                    int64_t first, int batch, float grad_scale, float* grad, float* loss_sum, void* stream);
 int vae21_trainer_adam(vae21_trainer* t, const float* grad, float lr_t, float beta1, float beta2, float eps, void* stream);
-/* One epoch on ONE GPU without returning to the host between batches: for every batch of `batch` rows of perm[0..n) (device int32
- * permutation, NULL = natural order) forward_backward with grad_scale = 1 / (n_out * rows) and adam with update number
- * iterations_before + 1, + 2, ... (lr_t computed per update as above).  Equivalent to the per-batch calls. */
+/* One epoch on ONE GPU in one call: for every batch of `batch` rows of perm[0..n) (device int32 permutation, NULL = natural
+ * order) steps 1 and 3 above with grad_scale = 1 / (n_out * rows) and update numbers iterations_before + 1, + 2, ...  Full batches
+ * replay one captured CUDA graph (batch number and learning rate are read from device memory).  Bitwise identical to the calls. */
 int vae21_trainer_epoch(vae21_trainer* t, const float* x_all, const float* y_all, const float* w_all, const int* perm, int64_t n, int batch,
                         float lr, float beta1, float beta2, float eps, int64_t iterations_before, float* loss_sum, void* stream);
 int vae21_trainer_launches(vae21_trainer* t, int64_t* n);
