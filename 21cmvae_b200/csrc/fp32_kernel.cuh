@@ -10,10 +10,21 @@
 //   weights stream from global/L2 through a cp.async ring of [KB][Npad] fp32 stages
 //   (host-packed, zero padded: Kpad % 8 == 0, Npad % 32 == 0);
 //   warp w owns rows 8w..8w+7 of the tile; lane t owns TN columns: 4 consecutive ones in each leading
-//   128-column block (one LDS.128 per k) plus one per remaining 32-column slot:
-//   per k a thread does 2 broadcast LDS.128 (its 8 rows) + TN/4 LDS.128 + (TN%4) LDS.32 and 8*TN FFMA.
+//   128-column block (one LDS.128 per k), then -- packed build, the default -- 2 consecutive ones in a 64-column block
+//   (one LDS.64) and at most one single column in a last 32-column slot.  Adjacent columns of a lane are accumulated in
+//   pairs by FFMA2 (`fma.rn.f32x2`, sm_100: two independent IEEE fmas per instruction, bit-identical to two FFMA):
+//   per k a thread does 2 broadcast LDS.128 (its 8 rows), TN/4 LDS.128 (+ LDS.64, + LDS.32), 8 register duplications of
+//   its row values and 8*(TN/2) FFMA2 (+ 8 FFMA for an odd column) -- about half the issue slots of the scalar build
+//   (VAE21_FP32_FFMA2=0: one column per remaining 32-column slot, 8*TN FFMA), 18.53 -> 17.90 ms per 1M rows on the same box.
 #pragma once
 #include "common.cuh"
+
+#ifndef VAE21_FP32_FFMA2
+#define VAE21_FP32_FFMA2 1
+#endif
+#ifndef VAE21_FP32_UNROLL
+#define VAE21_FP32_UNROLL 8
+#endif
 
 namespace f32k {
 
@@ -21,6 +32,7 @@ constexpr int MT = 64;        // rows per tile
 constexpr int LDA = MT + 4;   // 68: 16B-aligned rows; 17 x 16B chunks per row => conflict-free STS.128
 constexpr int KB = 8;         // k rows per weight stage
 constexpr int NTHREADS = 256;
+constexpr int KK_UNROLL = VAE21_FP32_UNROLL;  // unroll depth of the k loop inside a weight stage
 constexpr int MAX_SLOTS = 15; // columns per lane => widest layer 480
 
 struct Layer {
@@ -60,13 +72,35 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
     // Column ownership of a lane: the first NQ*128 columns in "quads" (4 consecutive columns, one LDS.128 per k),
     // the remaining NS 32-column slots one column each.  Slot j of the accumulator array is column col_of(j).
     constexpr int NQ = TN >> 2, NS = TN & 3;
+#if VAE21_FP32_FFMA2
+    // packed variant: two of the remaining slots form one 64-column block owned in column PAIRS (one LDS.64 per k), so that all
+    // but at most one column of a lane are accumulated by FFMA2 (fma.rn.f32x2: two independent IEEE fmas, same rounding as FFMA)
+    constexpr int NP = 2 * NQ + (NS >= 2 ? 1 : 0);  // column pairs per lane
+    constexpr bool ODD = (NS & 1) != 0;             // plus one single column
+    auto col_of = [&](int j) {
+        return j < 4 * NQ ? 128 * (j >> 2) + 4 * lane + (j & 3)
+                          : (j < 2 * NP ? 128 * NQ + 2 * lane + (j - 4 * NQ) : 128 * NQ + (NS >= 2 ? 64 : 0) + lane);
+    };
+#else
     auto col_of = [&](int j) { return j < 4 * NQ ? 128 * (j >> 2) + 4 * lane + (j & 3) : 128 * NQ + 32 * (j - 4 * NQ) + lane; };
+#endif
 
+#if VAE21_FP32_FFMA2
+    float2 acc2[8][NP > 0 ? NP : 1];
+    float acc1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        acc1[i] = 0.f;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) acc2[i][p] = make_float2(0.f, 0.f);
+    }
+#else
     float acc[8][TN];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+#endif
 
     auto load_stage = [&](int kb, int slot) {
         const float* src = Wl + static_cast<long long>(kb) * KB * Npad;
@@ -87,11 +121,43 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
         cp_async_commit();
         const float* ws = wst + (kb % WST) * stage_floats;
         const float* ap = in + (kb * KB) * LDA + 8 * warp;
-#pragma unroll
+#pragma unroll(KK_UNROLL)
         for (int kk = 0; kk < KB; ++kk) {
             const float4 a0 = *reinterpret_cast<const float4*>(ap + kk * LDA);
             const float4 a1 = *reinterpret_cast<const float4*>(ap + kk * LDA + 4);
             const float* wk = ws + kk * Npad;
+#if VAE21_FP32_FFMA2
+            float2 wp[NP > 0 ? NP : 1];
+            float w1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wk + 128 * q + 4 * lane);
+                wp[2 * q] = make_float2(w4.x, w4.y);
+                wp[2 * q + 1] = make_float2(w4.z, w4.w);
+            }
+            if (NS >= 2) wp[NP > 0 ? NP - 1 : 0] = *reinterpret_cast<const float2*>(wk + 128 * NQ + 2 * lane);
+            if (ODD) w1 = wk[128 * NQ + (NS >= 2 ? 64 : 0) + lane];
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float2 aa = make_float2(av[i], av[i]);
+#pragma unroll
+                for (int p = 0; p < NP; ++p) acc2[i][p] = __ffma2_rn(aa, wp[p], acc2[i][p]);
+                if (ODD) acc1[i] = fmaf(av[i], w1, acc1[i]);
+            }
+        }
+    }
+    float acc[8][TN];  // register renaming only: slot j of the epilogues below is column col_of(j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            acc[i][2 * p] = acc2[i][p].x;
+            acc[i][2 * p + 1] = acc2[i][p].y;
+        }
+        if (ODD) acc[i][TN - 1] = acc1[i];
+    }
+#else
             float wv[TN];
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
@@ -117,6 +183,7 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
             }
         }
     }
+#endif
 
     const float* Bl = Bg + L.b_off;
     if (!last) {
