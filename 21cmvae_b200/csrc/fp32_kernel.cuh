@@ -62,7 +62,8 @@ __device__ __forceinline__ void cp_async_wait() {
 template <int TN, int WST>
 __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float* __restrict__ Wg,
                                           const float* __restrict__ Bg, const float* in, float* outbuf, float* wst,
-                                          int stage_floats, const NormConsts& nc, const LaunchArgs& a, long long row0) {
+                                          int stage_floats, const NormConsts& nc, const LaunchArgs& a, long long row0,
+                                          long long next_w_off, int next_npad, int next_kpad, bool prefetched) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Npad = L.Npad;
     const float* Wl = Wg + L.w_off;
@@ -102,16 +103,37 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 #endif
 
+    // the lane's biases, fetched before the k loop so that the epilogue does not wait on L2 (bias arrays are padded to Npad)
+    float bv[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) bv[j] = __ldg(Bg + L.b_off + col_of(j));
+
     auto load_stage = [&](int kb, int slot) {
         const float* src = Wl + static_cast<long long>(kb) * KB * Npad;
         float* dst = wst + slot * stage_floats;
         for (int c = tid; c < chunks; c += NTHREADS) cp_async16(dst + 4 * c, src + 4 * c);
     };
 
+    if (!prefetched) {  // otherwise the previous layer issued these stages before its epilogue (see below)
 #pragma unroll
-    for (int s = 0; s < WST - 1; ++s) {
-        if (s < nkb) load_stage(s, s);
-        cp_async_commit();
+        for (int s = 0; s < WST - 1; ++s) {
+            if (s < nkb) load_stage(s, s);
+            cp_async_commit();
+        }
+    }
+    // After the k loop: start the first stages of the NEXT layer (of this tile, or layer 0 of the CTA's next tile) so that their
+    // L2 latency hides behind this layer's epilogue instead of opening the next layer.  One extra barrier frees the ring slots.
+#define PREFETCH_NEXT                                                                                        \
+    if (next_npad) {                                                                                           \
+        __syncthreads();                                                                                     \
+        const float* nsrc = Wg + next_w_off;                                                                 \
+        const int nchunks = (KB * next_npad) >> 2, nnkb = next_kpad / KB;                                    \
+        _Pragma("unroll") for (int s = 0; s < WST - 1; ++s) {                                                \
+            if (s < nnkb)                                                                                    \
+                for (int c = tid; c < nchunks; c += NTHREADS)                                                \
+                    cp_async16(wst + s * stage_floats + 4 * c, nsrc + static_cast<long long>(s) * KB * next_npad + 4 * c);  \
+            cp_async_commit();                                                                               \
+        }                                                                                                    \
     }
     for (int kb = 0; kb < nkb; ++kb) {
         cp_async_wait<WST - 2>();
@@ -147,6 +169,7 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
             }
         }
     }
+    PREFETCH_NEXT
     float acc[8][TN];  // register renaming only: slot j of the epilogues below is column col_of(j)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -183,14 +206,15 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
             }
         }
     }
+    PREFETCH_NEXT
 #endif
+#undef PREFETCH_NEXT
 
-    const float* Bl = Bg + L.b_off;
     if (!last) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
             const int n = col_of(j);
-            const float b = __ldg(Bl + n);
+            const float b = bv[j];
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -212,7 +236,7 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
             for (int j = 0; j < TN; ++j) {
                 const int n = col_of(j);
                 if (n < N) {
-                    const float b = __ldg(Bl + n), mu = __ldg(a.mu + n), ob = __ldg(a.obs + n), is = __ldg(a.isig + n);
+                    const float b = bv[j], mu = __ldg(a.mu + n), ob = __ldg(a.obs + n), is = __ldg(a.isig + n);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         float v = __fadd_rn(acc[i][j], b);
@@ -244,7 +268,7 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
             for (int j = 0; j < TN; ++j) {
                 const int n = col_of(j);
                 if (n < N) {
-                    const float b = __ldg(Bl + n), mu = __ldg(a.mu + n), in_band = __ldg(a.isig + n);
+                    const float b = bv[j], mu = __ldg(a.mu + n), in_band = __ldg(a.isig + n);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const long long row = rbase + i;
@@ -277,7 +301,7 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
             for (int j = 0; j < TN; ++j) {
                 const int n = col_of(j);
                 if (n < N) {
-                    const float b = __ldg(Bl + n);
+                    const float b = bv[j];
                     const float mu = denorm ? __ldg(a.mu + n) : 0.f;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -347,9 +371,15 @@ vae21_fp32_kernel(const Model m, const NormConsts nc, const LaunchArgs a, const 
             const float* in = (l & 1) ? buf1 : buf0;
             float* ob = (l & 1) ? buf0 : buf1;
             const int slots = L.Npad >> 5;
+            // weight-stage prefetch chain: every layer but the CTA's very first finds its leading stages already in flight
+            const int ln = last ? 0 : l + 1;
+            const bool has_next = !last || tile + gridDim.x < ntiles;
+            const long long nw = m.L[ln].w_off;
+            const int nn = has_next ? m.L[ln].Npad : 0, nk = m.L[ln].Kpad;
+            const bool pre = !(l == 0 && tile == static_cast<long long>(blockIdx.x));
 #define VAE21_CASE(T)                                                                             \
     case T:                                                                                       \
-        run_layer<T, WST>(L, last, Wg, Bg, in, ob, wst, stage_floats, nc, a, row0);               \
+        run_layer<T, WST>(L, last, Wg, Bg, in, ob, wst, stage_floats, nc, a, row0, nw, nn, nk, pre);\
         break;
             switch (slots) {
                 VAE21_CASE(1) VAE21_CASE(2) VAE21_CASE(3) VAE21_CASE(4) VAE21_CASE(5)
