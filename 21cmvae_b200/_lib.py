@@ -27,7 +27,7 @@ PRECISIONS = {"fp32": FP32_SIMT, "fp32_simt": FP32_SIMT, "tc": TC_BF16X3, "bf16x
 EXPORTS = [
     "vae21_version", "vae21_last_error", "vae21_device_count", "vae21_create", "vae21_destroy",
     "vae21_set_model", "vae21_set_norm", "vae21_predict", "vae21_forward_normalised", "vae21_chi2", "vae21_chi2_grid", "vae21_error",
-    "vae21_host_alloc", "vae21_host_free", "vae21_host_trim", "vae21_get_info", "vae21_time_predict",
+    "vae21_host_alloc", "vae21_host_free", "vae21_host_trim", "vae21_get_info", "vae21_get_tc_stats", "vae21_time_predict",
     "vae21_trainer_create", "vae21_trainer_destroy", "vae21_trainer_num_params", "vae21_trainer_set_params",
     "vae21_trainer_get_params", "vae21_trainer_forward_backward", "vae21_trainer_adam", "vae21_trainer_epoch", "vae21_trainer_launches",
 ]
@@ -76,6 +76,7 @@ def load() -> C.CDLL:
         lib.vae21_host_free.restype = None
         lib.vae21_host_trim.restype = None
         lib.vae21_get_info.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_float), C.POINTER(i32)]
+        lib.vae21_get_tc_stats.argtypes = [vp, C.POINTER(i64), i32]
         lib.vae21_time_predict.argtypes = [vp, vp, i32, i64, vp, i32, i32, C.POINTER(C.c_float)]
         lib.vae21_trainer_create.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(i32), i32, C.POINTER(vp)]
         lib.vae21_trainer_destroy.argtypes = [vp]
@@ -86,10 +87,8 @@ def load() -> C.CDLL:
         lib.vae21_trainer_adam.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp]
         lib.vae21_trainer_epoch.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float, i64, vp, vp]
         lib.vae21_trainer_launches.argtypes = [vp, C.POINTER(i64)]
-        for name in EXPORTS:
-            fn = getattr(lib, name)
-            if fn.restype is C.c_int and name not in ("vae21_version",):
-                pass
+        for name in EXPORTS:  # a stale libvae21.so must fail here, not at first use
+            getattr(lib, name)
         _lib = lib
         return lib
 
@@ -210,6 +209,13 @@ class Handle:
         _check(self._lib.vae21_get_info(self._h, C.byref(n), C.byref(ms), C.byref(tc)))
         return {"kernel_launches": n.value, "last_kernel_ms": ms.value, "tc_supported": bool(tc.value)}
 
+    def tc_saturation(self, reset=False) -> int:
+        """Epilogue threads that converted a hidden activation beyond the range of the fp16-based tensor-core operand formats
+        since the last reset (vae21_get_tc_stats); 0 = inside the range the error budget was pinned for."""
+        n = C.c_int64(0)
+        _check(self._lib.vae21_get_tc_stats(self._h, C.byref(n), int(bool(reset))))
+        return int(n.value)
+
     # -- compute
     def _prep_in(self, x, width):
         ptr, dev, shape, dt, didx, keep = _unwrap(x)
@@ -235,13 +241,17 @@ class Handle:
         return out, ptr, dev
 
     @staticmethod
-    def _stream_ptr(stream, on_device, keep):
+    def _stream_ptr(stream, *buffers):
+        """The CUDA stream the library must order its work against: the caller's `stream`, else the current torch stream of
+        the first device-resident torch tensor among `buffers` (input OR output -- a device input produced on that stream must
+        be complete before any library stream reads it), else the legacy default stream."""
         if stream is not None:
             return int(getattr(stream, "cuda_stream", stream))
-        if on_device and hasattr(keep, "is_cuda"):
-            import torch
+        for b in buffers:
+            if b is not None and getattr(b, "is_cuda", False):
+                import torch
 
-            return int(torch.cuda.current_stream(keep.device).cuda_stream)
+                return int(torch.cuda.current_stream(b.device).cuda_stream)
         return 0
 
     def predict(self, params, out=None, precision=FP32_SIMT, stream=None):
@@ -252,7 +262,7 @@ class Handle:
             raise TypeError(f"params dtype {dt} unsupported (float32/float64)")
         out, optr, odev = self._prep_out(out, n, self.dims[-1], keep.device if dev and hasattr(keep, "is_cuda") else None)
         _check(self._lib.vae21_predict(self._h, ptr, F64 if dt == np.float64 else F32, int(dev), n, optr, int(odev),
-                                       int(precision), self._stream_ptr(stream, dev and odev, keep)))
+                                       int(precision), self._stream_ptr(stream, keep, out)))
         return out
 
     def forward_normalised(self, x, out=None, precision=FP32_SIMT, stream=None):
@@ -263,7 +273,7 @@ class Handle:
             raise TypeError("normalised input must be float32")
         out, optr, odev = self._prep_out(out, n, self.dims[-1], keep.device if dev and hasattr(keep, "is_cuda") else None)
         _check(self._lib.vae21_forward_normalised(self._h, ptr, int(dev), n, optr, int(odev), int(precision),
-                                                  self._stream_ptr(stream, dev and odev, keep)))
+                                                  self._stream_ptr(stream, keep, out)))
         return out
 
     def chi2(self, params, obs, inv_sigma, out=None, want_chi2=True, want_best=True, precision=FP32_SIMT, stream=None):
@@ -287,7 +297,7 @@ class Handle:
         _check(self._lib.vae21_chi2(
             self._h, ptr, F64 if dt == np.float64 else F32, int(dev), n, obs.ctypes.data_as(C.POINTER(C.c_float)),
             isg.ctypes.data_as(C.POINTER(C.c_float)), optr, int(odev), C.byref(bv) if want_best else None,
-            C.byref(bi) if want_best else None, int(precision), self._stream_ptr(stream, dev and bool(odev), keep)))
+            C.byref(bi) if want_best else None, int(precision), self._stream_ptr(stream, keep, out)))
         return out, (bv.value if want_best else None), (bi.value if want_best else None)
 
     def error(self, params, truth, band_mask=None, relative=True, precision=FP32_SIMT):
@@ -310,7 +320,7 @@ class Handle:
         out = np.empty(n, np.float32)
         _check(self._lib.vae21_error(self._h, ptr, F64 if dt == np.float64 else F32, int(dev), n, tptr, int(tdev),
                                      mask.ctypes.data_as(C.POINTER(C.c_float)) if mask is not None else None, int(bool(relative)),
-                                     out.ctypes.data, 0, int(precision), None))
+                                     out.ctypes.data, 0, int(precision), self._stream_ptr(None, keep, tkeep) or None))
         return out
 
     def chi2_grid(self, npts, obs, inv_sigma, x_lo=None, x_hi=None, first=0, count=None, out=None, precision=FP32_SIMT, stream=None):

@@ -22,6 +22,7 @@ struct NormConsts {
     int floor_col;
     double floor_val;
     float sd;  // np.std(signal_train)
+    double pscale[VAE21_MAX_PAR];  // 2 / prange (tensor-core prologue: one fma instead of the reference's divide)
 };
 
 struct LaunchArgs {
@@ -32,6 +33,8 @@ struct LaunchArgs {
     const float* isig;   // [Nout] 1/sigma (device), chi2 mode
     float* chi2;         // [n] or nullptr
     unsigned long long* argmin_key;  // packed (float bits << 32 | row) running minimum, or nullptr
+    unsigned long long* sat;         // tensor-core paths: += number of epilogue threads that converted a hidden activation beyond the
+                                     // range of the operand format (fp16 hi: 65504; e4m3 corrections of fp16e4m3: 448); or nullptr
     // OUT_ERROR (emulator.py:129-192): chi2[r] = sqrt(mean_band((pred - truth[r])^2)) [* 100 / max_band |truth[r]| if err_relative];
     // the band is isig[k] in {0, 1}; err_inv_count = 1 / (number of bins in the band)
     const float* truth;  // [n, Nout] true signals (device)

@@ -11,8 +11,15 @@
 // comes from the fused parameter transform, the last layer's epilogue applies the output
 // transform (or the chi^2 reduction) and writes coalesced row segments.
 //
-// Warp roles (128 + 128 EPS threads): warp 0 = bulk-copy producer, warps 1 and 2 = MMA issuers (warp 1 also allocates TMEM),
-// warp 3 = prologue (parameter transform -> layer-0 operand, one tile ahead), warps 4.. = epilogue (thread = tile row = TMEM lane).
+// Warp roles (128 + 128 EPS threads): role 0 = bulk-copy producer, role 1 = MMA issuer (also allocates TMEM; in the follower CTA of a
+// pair it forwards "my half of this ring slot has landed" to the leader), roles 2 and 3 = prologue (parameter transform ->
+// layer-0 operand, one tile ahead, 64 rows each), roles 4.. = epilogue (thread = tile row = TMEM lane).
+//
+// Code size is a first-class constraint of this kernel: the four roles execute disjoint code, and when the whole kernel does not
+// fit the SM's instruction cache the lone MMA-issuing warp -- whose loop is re-fetched after every pass of the sixteen epilogue warps
+// through theirs -- stalls on instruction fetch for most of its time (round 2 measurement, profiles/README.md: 8.5 % of instruction
+// cache requests missed in the 135 KB round-1 kernel, and every instruction ADDED to the issue loop cost ~100 cycles).  Hence: the
+// output mode is a template parameter, every hot loop exists exactly once (no hand-unrolled copies), rare paths are __noinline__.
 //
 // Operand images (validated on hardware by tools/umma_probe.cu):
 //   un-swizzled K-major core-matrix layout [k/8][row][8 x 16-bit]: descriptor LBO = bytes between
@@ -53,17 +60,20 @@ constexpr int NFULL = 4;          // ring of "accumulator chunk ready" barriers
 #endif
 constexpr int DBG = VAE21_TC_ABLATE;
 #ifndef VAE21_TC_TIMING
-#define VAE21_TC_TIMING 0  // profiling only: per-CTA cycle counters of the first MMA warp's waits
+#define VAE21_TC_TIMING 0  // profiling only: per-CTA cycle counters of the MMA warp's waits (tools/tc_timing.py)
 #endif
 #if VAE21_TC_TIMING
-__device__ long long g_tc_timing[160][16];  // [cta][0 total, 1..5 operand-ready wait by consuming layer, 6..10 q_empty wait by layer, 11 ring, 12 rendezvous, 13 issue]
+__device__ long long g_tc_timing[160][16];  // [cta][0 total, 1 a0 wait, 2 accumulator-free wait, 3 ring wait, 4 operand wait, 5 issue blocks, 6 loop iterations]
 #endif
 constexpr int MAX_SLOTS = 16;
-#ifndef VAE21_TC_DIRECT_ARRIVE
-#define VAE21_TC_DIRECT_ARRIVE 1  // pair kernel: 1 = the follower's epilogue warps arrive on the leader's barriers themselves,
-#endif                            // 0 = they arrive locally and the follower's idle MMA warp forwards one arrival per event
+#ifndef VAE21_TC_CTRL_LAST
+#define VAE21_TC_CTRL_LAST 1  // control warps on the highest hardware warp ids (see the kernel)
+#endif
 #ifndef VAE21_TC_KPS
 #define VAE21_TC_KPS 2   // k-steps per ring slot of the CTA-pair kernel (1 or 2; 1 measured slower: 2.05 vs 1.90 ms)
+#endif
+#ifndef VAE21_TC_WAIT_HINT
+#define VAE21_TC_WAIT_HINT 0  // ns the hardware may suspend a warp inside mbarrier.try_wait (0 = no hint)
 #endif
 constexpr int BAR_BYTES = 512;  // barrier block at off_bar (2 * MAX_SLOTS + NFULL + 2 + MAX_LCHUNK + 1 barriers + the TMEM base word)
 constexpr int MAX_LCHUNK = 4;      // chunks per non-final layer (per-chunk operand-ready barriers)
@@ -312,7 +322,7 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
     P.slot_bytes2 = P.slot_bytes / 2 * VAE21_TC_KPS;
     P.nslots2 = std::min(MAX_SLOTS, avail / P.slot_bytes2) & ~1;  // even: the MMA loop consumes slots in pairs
     // narrow chunks would leave most of a slot empty (112 columns: half): pack up to 4 k-steps of this CTA's half tile into a slot
-    static const int kps_max = std::getenv("VAE21_TC_KPS_MAX") ? std::atoi(std::getenv("VAE21_TC_KPS_MAX")) : 4;
+    static const int kps_max = std::getenv("VAE21_TC_KPS_MAX") ? std::min(4, std::atoi(std::getenv("VAE21_TC_KPS_MAX"))) : 4;  // the issue loop unrolls 4
     for (int c = 0; c < nchunks; ++c)
         P.C[c].kps2 = std::max(VAE21_TC_KPS, std::min(std::max(kps_max, VAE21_TC_KPS), P.slot_bytes2 / (P.C[c].ncols * 32)));
     P.smem_total2 = off + P.nslots2 * P.slot_bytes2 + 128;
@@ -452,10 +462,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
+#if VAE21_TC_WAIT_HINT
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+#else
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
             "selp.u32 %0, 1, 0, p;\n\t}\n"
             : "=r"(ok)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(static_cast<uint32_t>(VAE21_TC_WAIT_HINT))
             : "memory");
         if (ok) return;
         if ((++spins & 1023u) == 0) {  // deadlock guard: a scheduling bug must fault, not hang the GPU
@@ -610,17 +624,7 @@ __device__ __forceinline__ uint32_t mbar_try_cluster(uint32_t bar, uint32_t pari
         : "memory");
     return ok;
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    long long t0 = 0;
-    unsigned spins = 0;
-    while (!mbar_try_cluster(bar, parity)) {
-        if ((++spins & 1023u) == 0) {
-            const long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 8000000000ll) __trap();
-        }
-    }
-}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void mma2_ss2(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
@@ -665,6 +669,13 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ float relu_nan(float v) {  // max that propagates NaN like np.maximum / tf.nn.relu
     float r;
     asm("max.NaN.f32 %0, %1, %2;\n" : "=f"(r) : "f"(v), "f"(0.f));
+    return r;
+}
+
+// max(a, |b|, |c|) in one instruction (sm_100 three-input max; NaN operands are ignored like fmaxf)
+__device__ __forceinline__ float fmax3_abs(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;\n" : "=f"(r) : "f"(a), "f"(fabsf(b)), "f"(fabsf(c)));
     return r;
 }
 
@@ -720,11 +731,76 @@ __device__ __forceinline__ void split16(const float (&v)[16], uint32_t (&w)[16])
 // ---------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------
+// One k-step of one accumulator chunk: the kind::f16 hi x hi product plus the correction MMA(s) of the operand format.
+//   TS (A operand in TMEM):  a = TMEM column of the 16-bit hi pairs, a2 = a + 8 (second operand part)
+//   SS (A operand in smem):  a = low descriptor word of the hi tile, a2 = of the second tile
+//   b / b2: low descriptor words of the weight hi tile / second tile; `hi` = constant high descriptor word
+template <int FMT, bool PAIR>
+__device__ __forceinline__ void kstep_mma(bool ts, uint32_t d, uint32_t a, uint32_t a2, uint32_t b, uint32_t b2, uint32_t hi, uint32_t idesc,
+                                          uint32_t acc0) {
+    if (ts) {
+        if (FMT == 2) {
+            if (PAIR) { mma2_ts2(d, a, b, hi, idesc, acc0); mma8x2_ts2(d, a2, b2, hi, idesc, 1u); }
+            else { mma_ts2(d, a, b, hi, idesc, acc0); mma8_ts2(d, a2, b2, hi, idesc, 1u); }
+        } else if (PAIR) {
+            mma2_ts2(d, a, b, hi, idesc, acc0); mma2_ts2(d, a, b2, hi, idesc, 1u); mma2_ts2(d, a2, b, hi, idesc, 1u);
+        } else {
+            mma_ts2(d, a, b, hi, idesc, acc0); mma_ts2(d, a, b2, hi, idesc, 1u); mma_ts2(d, a2, b, hi, idesc, 1u);
+        }
+    } else {
+        if (FMT == 2) {
+            if (PAIR) { mma2_ss2(d, a, b, hi, idesc, acc0); mma8x2_ss2(d, a2, b2, hi, idesc, 1u); }
+            else { mma_ss2(d, a, b, hi, idesc, acc0); mma8_ss2(d, a2, b2, hi, idesc, 1u); }
+        } else if (PAIR) {
+            mma2_ss2(d, a, b, hi, idesc, acc0); mma2_ss2(d, a, b2, hi, idesc, 1u); mma2_ss2(d, a2, b, hi, idesc, 1u);
+        } else {
+            mma_ss2(d, a, b, hi, idesc, acc0); mma_ss2(d, a, b2, hi, idesc, 1u); mma_ss2(d, a2, b, hi, idesc, 1u);
+        }
+    }
+}
+
+// The parameter transform of one row (preprocess.py:74-78, :105-108): floor substitution and log10 in fp64 like the reference and the
+// FP32 path, then ONE fp64 fma for the affine map x = (t - pmin) * (2 / prange) - 1 (the reference divides: the two differ by at most
+// one fp64 rounding, far below the fp32 cast that follows and irrelevant at the tensor-core tolerance).  Out of line: it contains
+// the double-precision log10 and runs in the two prologue warps only.
+__device__ __noinline__ void prologue_row(const LaunchArgs& a, const NormConsts& nc, long long grow, int K0, float* x /*[16]*/) {
+#pragma unroll 1
+    for (int j = 0; j < 16; ++j) x[j] = 0.f;
+    if (grow >= a.n) return;
+    if (a.in_mode == IN_GRID) {
+        grid_point(a, static_cast<unsigned long long>(a.row_base + grow), K0, x);
+        return;
+    }
+#pragma unroll 1
+    for (int j = 0; j < K0; ++j) {
+        const long long g = grow * K0 + j;
+        if (a.in_mode == IN_NORMALISED_F32) {
+            x[j] = reinterpret_cast<const float*>(a.in)[g];
+            continue;
+        }
+        const bool f32_in = (a.in_mode == IN_PARAMS_F32);
+        double p = f32_in ? static_cast<double>(reinterpret_cast<const float*>(a.in)[g]) : reinterpret_cast<const double*>(a.in)[g];
+        if (j == nc.floor_col && p == 0.0) p = f32_in ? static_cast<double>(static_cast<float>(nc.floor_val)) : nc.floor_val;
+        double t = p;
+        if (nc.log_mask[j]) {
+            t = log10(p);
+            if (f32_in) t = static_cast<double>(static_cast<float>(t));  // numpy takes the log of a float32 array in float32
+        }
+        x[j] = static_cast<float>(fma(t - nc.pmin[j], nc.pscale[j], -1.0));
+    }
+}
+
+// Output modes as a template parameter (each instantiation carries only its own final-layer code):
+enum : int { OM_ROWS = 0 /* OUT_PREDICT / OUT_NORMALISED: spectra written */, OM_CHI2 = 1, OM_ERROR = 2 };
+
+// hidden activations beyond this magnitude leave the range of the 8-bit / 16-bit operand parts (counted, see LaunchArgs::sat)
+template <int FMT>
+__device__ __forceinline__ constexpr float sat_limit() { return FMT == 2 ? 480.f : 65504.f; }
+
 // CG = 1: one CTA per 128-row tile (cta_group::1).  CG = 2: a cluster of two CTAs works on a 256-row
 // super-tile with cta_group::2 MMAs (M = 256): rank 0 issues every MMA for both CTAs, each CTA streams
 // HALF of every weight tile into its own shared memory and runs its own epilogue on its own 128 rows.
-// The MMA-issuing warp -- the limiter of the one-CTA kernel -- then serves twice the rows per instruction.
-template <int FMT, int CG>  // FMT 0: bf16 split (3 MMAs per k-step), 1: fp16 split (3), 2: fp16 + e4m3 corrections (2)
+template <int FMT, int CG, int OM>  // FMT 0: bf16 split (3 MMAs per k-step), 1: fp16 split (3), 2: fp16 + e4m3 corrections (2)
 __global__ void __launch_bounds__(NTHREADS, 1)
 vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormConsts nc, const __grid_constant__ LaunchArgs a,
                 const uint8_t* __restrict__ wimg, const float* __restrict__ bias_g) {
@@ -733,7 +809,18 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     const uint32_t base = (raw + 127u) & ~127u;  // shared-window address of the carve-up
     uint8_t* sm = smem_raw + (base - raw);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // `warp` is the ROLE index (0 producer, 1 MMA, 2-3 prologue, 4.. epilogue); the epilogue role 4 + e runs on hardware
+    // warp e (VAE21_TC_CTRL_LAST, measured neutral), so its TMEM sub-partition (hardware warp id mod 4) is still `warp & 3`.
+    // The hardware warp index goes through a shuffle so that the compiler can PROVE it warp-uniform: the role branches below are then
+    // uniform branches, and the loop counters, chunk records and MMA descriptors of the control warps live in uniform registers
+    // instead of being moved there (R2UR) before every tcgen05 instruction.
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int hw_warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+#if VAE21_TC_CTRL_LAST
+    const int warp = hw_warp < NEPI / 32 ? hw_warp + 4 : hw_warp - NEPI / 32;
+#else
+    const int warp = hw_warp;
+#endif
     constexpr bool PAIR = (CG == 2);
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = (rank == 0);
@@ -751,10 +838,8 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     const uint32_t bar_a0_ready = bar0 + 8u * (2 * MAX_SLOTS + NFULL + 2 + MAX_LCHUNK);
     const uint32_t bar_a0_free = bar0 + 8u * (2 * MAX_SLOTS + NFULL + 3 + MAX_LCHUNK);  // layer-0 MMAs of the tile have read a0
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + P.off_bar + 8 * (2 * MAX_SLOTS + NFULL + 4 + MAX_LCHUNK));
-    float* s_pmin = reinterpret_cast<float*>(sm + P.off_bar + BAR_BYTES);   // [16] fp32 copies of the prologue constants
-    float* s_pscale = s_pmin + 16;                                    // [16] 2 / (pmax - pmin)
-    float* s_chi = s_pscale + 16;                                     // [2][EPS-1][128] chi^2 partials of the other column shares
-    float* s_amp = s_chi + 2 * (EPS - 1) * 128;                       // [2][EPS-1][128] |truth| maxima (OUT_ERROR)
+    float* s_chi = reinterpret_cast<float*>(sm + P.off_bar + BAR_BYTES) + 32;  // [2][EPS-1][128] chi^2 partials of the other column shares
+    float* s_amp = s_chi + 2 * (EPS - 1) * 128;                                 // [2][EPS-1][128] |truth| maxima (OM_ERROR)
 
     float* s_bias = reinterpret_cast<float*>(sm + P.off_bias);
     float* s_s0 = reinterpret_cast<float*>(sm + P.off_s0);
@@ -768,21 +853,15 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             mbar_init(bar_ring_full(s), (PAIR && leader) ? 2 : 1);
             mbar_init(bar_ring_empty(s), 1);
         }
-        // epilogue -> MMA hand-offs: ONE arrival per epilogue warp (elected lane after __syncwarp), not one per thread.  In a
-        // pair the follower's epilogue warps arrive DIRECTLY on the leader's barriers (remote arrive), so those count both CTAs.
-        const uint32_t both = (PAIR && leader && VAE21_TC_DIRECT_ARRIVE) ? 2u : 1u;
-        const uint32_t fwd = (PAIR && leader && !VAE21_TC_DIRECT_ARRIVE) ? 1u : 0u;
-        for (int i = 0; i < NFULL; ++i) mbar_init(bar_chunk_full(i), P.issuers);
-        for (int b = 0; b < 2; ++b) mbar_init(bar_q_empty(b), (NEPI / 32) * both + fwd);
-        // (chunk_full: one commit from each of the two issuing warps)
-        for (int j = 0; j < MAX_LCHUNK; ++j) mbar_init(bar_act_ready(j), (NEPI / 32) * both + fwd);
-        mbar_init(bar_a0_ready, 1 * both + fwd);  // one arrival from the prologue warp (of each CTA)
-        mbar_init(bar_a0_free, P.issuers);
+        // epilogue -> MMA hand-offs: ONE arrival per epilogue warp (elected lane after __syncwarp).  In a pair the follower's epilogue
+        // warps arrive DIRECTLY on the leader's barriers (remote arrive), so those count both CTAs.
+        const uint32_t both = (PAIR && leader) ? 2u : 1u;
+        for (int i = 0; i < NFULL; ++i) mbar_init(bar_chunk_full(i), 1);
+        for (int b = 0; b < 2; ++b) mbar_init(bar_q_empty(b), (NEPI / 32) * both);
+        for (int j = 0; j < MAX_LCHUNK; ++j) mbar_init(bar_act_ready(j), (NEPI / 32) * both);
+        mbar_init(bar_a0_ready, 2 * both);  // one arrival from each of the two prologue warps (of each CTA)
+        mbar_init(bar_a0_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    if (tid < 16) {
-        s_pmin[tid] = tid < nc.n_par ? static_cast<float>(nc.pmin[tid]) : 0.f;
-        s_pscale[tid] = tid < nc.n_par ? static_cast<float>(2.0 / nc.prange[tid]) : 0.f;
     }
     {
         const Layer& LL = P.L[P.n_layers - 1];
@@ -793,11 +872,11 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             float s0 = b, ob = 0.f, is = 0.f;
             if (n < P.n_out) {
                 if (a.out_mode != OUT_NORMALISED) s0 = fmaf(b, nc.sd, a.mu[n]);
-                if (a.out_mode == OUT_CHI2) {
+                if (OM == OM_CHI2) {
                     ob = a.obs[n];
                     is = a.isig[n];
                 }
-                if (a.out_mode == OUT_ERROR) is = a.isig[n];  // 1 inside the frequency band, 0 outside
+                if (OM == OM_ERROR) is = a.isig[n];  // 1 inside the frequency band, 0 outside
             }
             s_s0[n] = s0;
             s_obs[n] = ob;
@@ -820,36 +899,32 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     const uint32_t tm = *tmem_slot;
     const int n_chunks = P.n_chunks, nslots = PAIR ? P.nslots2 : P.nslots;
     const uint32_t ring0 = base + P.off_ring, slot_bytes = static_cast<uint32_t>(PAIR ? P.slot_bytes2 : P.slot_bytes);
-    const uint32_t slot16 = slot_bytes >> 4;
 
     if (warp == 0) {
         // ===================== producer: stream the weight image through the ring ============
-        if (lane == 0 && !(DBG & 128)) {
+        if (lane == 0) {
             int slot = 0;
             uint32_t phase = 0;
+            const uint8_t* img = PAIR ? wimg + P.w_bytes + static_cast<size_t>(rank) * (P.w_bytes / 2) : wimg;
+#pragma unroll 1
             for (long long unit = unit0; unit < nunits; unit += ustep) {
+#pragma unroll 1
                 for (int c = 0; c < n_chunks; ++c) {
                     const Chunk& C = P.C[c];
-                    const uint32_t bytes = static_cast<uint32_t>(C.ncols) * (PAIR ? 32u : 64u);
-                    const uint8_t* src = PAIR ? wimg + P.w_bytes + static_cast<size_t>(rank) * (P.w_bytes / 2) + C.w_off / 2
-                                              : wimg + C.w_off;
-                    const int nst = C.nstages;
-                    const int kps = PAIR ? C.kps2 : 1;
+                    const uint32_t bytes = static_cast<uint32_t>(C.ncols) * (PAIR ? 32u : 64u);  // one k-step of this CTA's rows
+                    const uint8_t* src = img + (PAIR ? C.w_off / 2 : C.w_off);
+                    const int nst = C.nstages, kps = PAIR ? C.kps2 : 1;
+#pragma unroll 1
                     for (int s = 0; s < nst; s += kps) {
                         const uint32_t sbytes = bytes * static_cast<uint32_t>(min(kps, nst - s));  // k-steps in this slot
                         mbar_wait(bar_ring_empty(slot), phase ^ 1u);
-                        if (DBG & 4) {
-                            mbar_arrive(bar_ring_full(slot));
-                        } else {
                         mbar_expect_tx(bar_ring_full(slot), sbytes);
                         asm volatile(
                             "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
                                 ring0 + slot * slot_bytes),
                             "l"(src), "r"(sbytes), "r"(bar_ring_full(slot))
                             : "memory");
-                        }
-                        src += sbytes - bytes;
-                        src += bytes;
+                        src += sbytes;
                         if (++slot == nslots) {
                             slot = 0;
                             phase ^= 1u;
@@ -858,19 +933,33 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 }
             }
         }
-    } else if (warp == 1 || warp == 2) {
-        // ===================== MMA issuers ===================================================
-        // Two warps share the issue work (one warp alone is the limiter: ~100 instructions per 6 MMAs at the
-        // latency-bound rate of a lone warp).  Within an accumulator chunk warp mw issues the pair-iterations
-        // with (iteration & 1) == mw.  Ordering between the two issuers is established once per chunk: after
-        // warp 0 has issued iteration 0 (which overwrites the accumulator) both meet at a named barrier bracketed
-        // by tcgen05 fences, so everything warp 1 issues is ordered after it.
-        const int mw = warp - 1;
-        const bool two_issuers = (P.issuers == 2);
-        if (two_issuers || mw == 0) {
-        // The whole warp runs this (warp-uniform) loop and only the tcgen05 instructions are
-        // predicated on one elected lane: measured with tools/umma_probe.cu, a loop inside an
-        // `if (lane == 0)` branch costs 269 cycles per MMA, this form 96..131.
+    } else if (warp == 1 && PAIR && !leader) {
+        // ===================== follower of a pair: relay "my half of this ring slot has landed" to the issuer =========
+        // (a bulk copy cannot signal a barrier in another CTA; the leader's MMAs read both CTAs' halves)
+        int slot = 0;
+        uint32_t rphase = 0;
+#pragma unroll 1
+        for (long long unit = unit0; unit < nunits; unit += ustep) {
+#pragma unroll 1
+            for (int c = 0; c < n_chunks; ++c) {
+                const int nst = P.C[c].nstages, kps = P.C[c].kps2;
+#pragma unroll 1
+                for (int s = 0; s < nst; s += kps) {
+                    mbar_wait(bar_ring_full(slot), rphase);
+                    if (lane == 0) mbar_arrive_remote(bar_ring_full(slot), 0);
+                    __syncwarp();
+                    if (++slot == nslots) {
+                        slot = 0;
+                        rphase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer ====================================================
+        // ONE warp issues every tcgen05.mma of the CTA (pair), in program order: the accumulation order -- hence every output bit --
+        // is fixed (tcgen05 instructions of different threads are unordered).  The whole warp runs the (warp-uniform) loop, only the
+        // tcgen05 instructions are predicated on one elected lane.  One ring slot (1..4 k-steps) per iteration.
         int slot = 0;
         uint32_t rphase = 0;
         uint32_t seq = 0;                 // running chunk counter (chunk_full ring)
@@ -882,34 +971,23 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         // descriptor high words are constant: SBO = 128 B, version 1; LBO goes into the low word
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);
         const uint32_t a_lbo = (static_cast<uint32_t>(A_KG_BYTES) >> 4) << 16;
-        // In the CTA-pair kernel rank 0 issues; rank 1 runs the SAME schedule as a forwarder: wherever the
-        // issuer waits for an event, the forwarder waits for its own CTA's instance of it and then arrives on
-        // the issuer's barrier (which counts the local arrivals plus this one).
+        const uint32_t slot16 = slot_bytes >> 4;
 #if VAE21_TC_TIMING
-        long long tm_total = clock64(), tm_evt[5] = {0, 0, 0, 0, 0}, tm_q[5] = {0, 0, 0, 0, 0}, tm_ring = 0, tm_rdv = 0, tm_issue = 0, tm_setup = 0, tm_it_mine = 0, tm_it_other = 0;
+        long long tm_total = clock64(), tm_a0 = 0, tm_q = 0, tm_ring = 0, tm_opnd = 0, tm_issue = 0, tm_iter = 0;
 #define TSTART const long long t_s_ = clock64();
 #define TADD(var) var += clock64() - t_s_;
 #else
 #define TSTART
 #define TADD(var)
 #endif
-        auto sync_event = [&](uint32_t bar, uint32_t parity) {
-            if (!PAIR) {
-                mbar_wait(bar, parity);
-            } else if (leader) {
-                mbar_wait_cluster(bar, parity);
-            } else if (!VAE21_TC_DIRECT_ARRIVE) {
-                mbar_wait(bar, parity);
-                if (mw == 0 && lane == 0) mbar_arrive_remote(bar, 0);
-                __syncwarp();
-            }
-            // (direct mode: the follower's epilogue warps signal the leader themselves; the forwarder only relays ring slots)
+        auto wait_ev = [&](uint32_t bar, uint32_t parity) {
+            if (PAIR) mbar_wait_cluster(bar, parity);
+            else mbar_wait(bar, parity);
         };
+#pragma unroll 1
         for (long long unit = unit0; unit < nunits; unit += ustep) {
+#pragma unroll 1
             for (int c = 0; c < n_chunks; ++c) {
-#if VAE21_TC_TIMING
-                const long long t_chunk0 = clock64();
-#endif
                 const Chunk& C = P.C[c];
                 // Operand readiness is tracked per chunk of the PRODUCING layer: k-step s of this layer only needs
                 // the 16 features [16 s, 16 s + 16), so the first chunk of a layer starts as soon as the first chunk of
@@ -917,7 +995,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 int src = -1, src_end = -1;  // chunks of the producing layer still to wait for
                 if (C.idx_in_layer == 0) {
                     if (C.layer == 0) {
-                        { TSTART sync_event(bar_a0_ready, a0_cnt & 1u); TADD(tm_evt[0]) }
+                        { TSTART wait_ev(bar_a0_ready, a0_cnt & 1u); TADD(tm_a0) }
                         ++a0_cnt;
                     } else {
                         src = C.src_first;
@@ -927,248 +1005,103 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 if (C.qbuf >= 0) {  // accumulator buffer must have been drained by the epilogue
                     const uint32_t u = C.qbuf ? q_use1 : q_use0;
                     if (C.qbuf) ++q_use1; else ++q_use0;
-                    if (u > 0) { TSTART sync_event(bar_q_empty(C.qbuf), (u - 1u) & 1u); TADD(tm_q[C.layer < 5 ? C.layer : 4]) }
-                }
-                // chunk-start rendezvous of the two issuers: every MMA of earlier chunks (either warp) is ordered before
-                // the first MMA of this chunk, which may overwrite TMEM columns those MMAs read
-                if (two_issuers) {
-                    TSTART
-                    tc_fence_before();
-                    asm volatile("bar.sync 2, 64;\n" ::: "memory");
-                    tc_fence_after();
-                    TADD(tm_rdv)
+                    if (u > 0) { TSTART wait_ev(bar_q_empty(C.qbuf), (u - 1u) & 1u); TADD(tm_q) }
                 }
                 const uint32_t idesc = idesc_base | (static_cast<uint32_t>(C.ncols >> 3) << 17);
                 const uint32_t d = tm + static_cast<uint32_t>(C.dcol);
                 const uint32_t b_kg = static_cast<uint32_t>(C.ncols / CG) * 16u;  // bytes between B k-groups (this CTA's rows)
-                const uint32_t b_lo16 = (b_kg * 2u) >> 4;                         // hi tile -> lo tile, in 16 B units
+                const uint32_t b_lo16 = (b_kg * 2u) >> 4;                         // hi tile -> second tile, in 16 B units
+                const uint32_t kstep16 = b_kg * 4u >> 4;                          // one k-step of this CTA's B rows, in 16 B units
                 // low descriptor words: (address >> 4) | (LBO >> 4) << 16; slots are slot16 apart
                 const uint32_t b_base32 = ((ring0 & 0x3FFFFu) >> 4) | ((b_kg >> 4) << 16);
                 const bool ts = (C.a_src == A_TMEM);
-                uint32_t a_lo32 = (((base + (C.a_src == A_SMEM_A0 ? P.off_a0 : P.off_act)) & 0x3FFFFu) >> 4) | a_lbo;
-                uint32_t ta = tm;
-                const int nst = C.nstages;
+                // A operand cursor: TMEM column (16 per k-step) or low descriptor word (KSTEP_BYTES per k-step)
+                uint32_t acur = ts ? tm : ((((base + (C.a_src == A_SMEM_A0 ? P.off_a0 : P.off_act)) & 0x3FFFFu) >> 4) | a_lbo);
+                const uint32_t astep = ts ? 16u : static_cast<uint32_t>(KSTEP_BYTES >> 4);
+                const uint32_t a2off = ts ? 8u : ((2u * A_KG_BYTES) >> 4);
+                const int nst = C.nstages, kps = PAIR ? C.kps2 : 1;
                 int next_src_k = (src >= 0) ? 0 : 0x7fffffff;  // k-step at which the next producing chunk starts
-                const uint32_t kstep16 = b_kg * 4u >> 4;  // one k-step of this CTA's B rows ({hi, lo} tiles), 16 B units
-#if VAE21_TC_TIMING
-                tm_setup += clock64() - t_chunk0;
-#endif
-                const int kps = PAIR ? C.kps2 : 1;  // k-steps per ring slot
-                for (int s = 0, it = 0; s < nst; s += 2 * kps, ++it) {
+#pragma unroll 1
+                for (int s = 0; s < nst; s += kps) {
 #if VAE21_TC_TIMING
                     const long long t_it0 = clock64();
 #endif
-                    const int nk = min(2 * kps, nst - s);  // k-steps of this iteration (two ring slots' worth)
-                    const bool two = (nk > kps);           // second slot in use
-                    // the k-steps of this iteration may cross into the next chunk of the producing layer (both issuers pass these
-                    // waits; the one that issues this iteration does so AFTER its ring-slot waits, which are normally already
-                    // satisfied -- the producer runs ahead -- so that nothing but the MMA issue follows the operand wake-up)
-                    auto wait_operands = [&]() {
-                        if (s + nk - 1 >= next_src_k) {
-                            do {
-                                const int j = src - C.src_first;
-                                { TSTART sync_event(bar_act_ready(j), (act_cnt[j]++) & 1u); TADD(tm_evt[C.layer < 5 ? C.layer : 4]) }
-                                ++src;
-                                next_src_k = (src < src_end) ? (P.C[src].n0 >> 4) : 0x7fffffff;
-                            } while (s + nk - 1 >= next_src_k);
-                            tc_fence_after();
-                        }
-                    };
-                    int slot1 = slot + 1;
-                    uint32_t ph1 = rphase;
-                    if (slot1 == nslots) {
-                        slot1 = 0;
-                        ph1 ^= 1u;
-                    }
-                    const uint32_t full0 = bar0 + 8u * slot, full1 = bar0 + 8u * slot1;
-                    const bool mine = !two_issuers || ((it & 1) == mw);
-                    if (!mine) {
-                        wait_operands();  // the other issuing warp handles this iteration
-                    } else if ((DBG & 128) && PAIR && !leader) {
-                        wait_operands();
-                    } else if (PAIR && !leader) {
-                        wait_operands();
-                        // forwarder: my halves of these stages have landed -> tell the issuer
-                        mbar_wait(full0, rphase);
-                        if (lane == 0) mbar_arrive_remote(full0, 0);
-                        if (two) {
-                            mbar_wait(full1, ph1);
-                            if (lane == 0) mbar_arrive_remote(full1, 0);
-                        }
-                        __syncwarp();
-                    } else {
-                        // probe both stages' barriers back to back (their ~90-cycle latencies overlap)
-                        {
-                            TSTART
-                            uint32_t ok = (DBG & 128) ? 1u : mbar_try(full0, rphase);
-                            if (two && !(DBG & 128)) ok &= mbar_try(full1, ph1);
-                            if (!ok) {
-                                mbar_wait(full0, rphase);
-                                if (two) mbar_wait(full1, ph1);
-                            }
-                            TADD(tm_ring)
-                        }
-                        wait_operands();
-                        tc_fence_after();
-#if VAE21_TC_TIMING
-                        const long long t_issue0 = clock64();
-#endif
-                        const uint32_t bs0 = b_base32 + slot * slot16, bs1 = b_base32 + slot1 * slot16;
-                        if (elect_one()) {
-                            // one k-step: kind::f16 hi x hi plus the correction MMA(s) of the operand format
-                            auto kstep = [&](int j, uint32_t bj) {
-                                const uint32_t acc0 = (s + j) > 0 ? 1u : 0u;
-                                if (DBG & 1) return;
-                                if (ts) {
-                                    const uint32_t taj = ta + 16u * j;
-                                    if (FMT == 2) {
-                                        if (PAIR) {
-                                            mma2_ts2(d, taj, bj, desc_hi, idesc, acc0);
-                                            mma8x2_ts2(d, taj + 8u, bj + b_lo16, desc_hi, idesc, 1u);
-                                        } else {
-                                            mma_ts2(d, taj, bj, desc_hi, idesc, acc0);
-                                            mma8_ts2(d, taj + 8u, bj + b_lo16, desc_hi, idesc, 1u);
-                                        }
-                                    } else if (PAIR) {
-                                        mma2_ts2(d, taj, bj, desc_hi, idesc, acc0);
-                                        mma2_ts2(d, taj, bj + b_lo16, desc_hi, idesc, 1u);
-                                        mma2_ts2(d, taj + 8u, bj, desc_hi, idesc, 1u);
-                                    } else {
-                                        mma_ts2(d, taj, bj, desc_hi, idesc, acc0);
-                                        mma_ts2(d, taj, bj + b_lo16, desc_hi, idesc, 1u);
-                                        mma_ts2(d, taj + 8u, bj, desc_hi, idesc, 1u);
-                                    }
-                                } else {
-                                    const uint32_t aj = a_lo32 + static_cast<uint32_t>(j) * (KSTEP_BYTES >> 4);
-                                    const uint32_t aj_lo = aj + ((2u * A_KG_BYTES) >> 4);
-                                    if (FMT == 2) {
-                                        if (PAIR) {
-                                            mma2_ss2(d, aj, bj, desc_hi, idesc, acc0);
-                                            mma8x2_ss2(d, aj_lo, bj + b_lo16, desc_hi, idesc, 1u);
-                                        } else {
-                                            mma_ss2(d, aj, bj, desc_hi, idesc, acc0);
-                                            mma8_ss2(d, aj_lo, bj + b_lo16, desc_hi, idesc, 1u);
-                                        }
-                                    } else if (PAIR) {
-                                        mma2_ss2(d, aj, bj, desc_hi, idesc, acc0);
-                                        mma2_ss2(d, aj, bj + b_lo16, desc_hi, idesc, 1u);
-                                        mma2_ss2(d, aj_lo, bj, desc_hi, idesc, 1u);
-                                    } else {
-                                        mma_ss2(d, aj, bj, desc_hi, idesc, acc0);
-                                        mma_ss2(d, aj, bj + b_lo16, desc_hi, idesc, 1u);
-                                        mma_ss2(d, aj_lo, bj, desc_hi, idesc, 1u);
-                                    }
-                                }
-                            };
-                            // first ring slot of this iteration, then (if in use) the second; each slot is freed -- in both CTAs of a
-                            // pair -- by a commit behind the MMAs of its last k-step
-                            const int n0k = min(nk, kps);
-#pragma unroll 4
-                            for (int j = 0; j < n0k; ++j) kstep(j, bs0 + static_cast<uint32_t>(j) * kstep16);
-                            if (!(DBG & 128)) {
-                                if (PAIR) mma2_commit_both(full0 + 8u * MAX_SLOTS);
-                                else mma_commit(full0 + 8u * MAX_SLOTS);
-                            }
-                            if (two) {
-#pragma unroll 4
-                                for (int j = kps; j < nk; ++j) kstep(j, bs1 + static_cast<uint32_t>(j - kps) * kstep16);
-                                if (!(DBG & 128)) {
-                                    if (PAIR) mma2_commit_both(full1 + 8u * MAX_SLOTS);
-                                    else mma_commit(full1 + 8u * MAX_SLOTS);
-                                }
-                            }
-                        }
-                        __syncwarp();
-#if VAE21_TC_TIMING
-                        tm_issue += clock64() - t_issue0;
-#endif
-                    }
-                    if (s == 0 && two_issuers) {
+                    const int nk = min(kps, nst - s);
+                    const uint32_t full = bar_ring_full(slot);
+                    { TSTART if (!mbar_try(full, rphase)) mbar_wait(full, rphase); TADD(tm_ring) }
+                    if (s + nk - 1 >= next_src_k) {  // the k-steps of this slot reach into the next chunk of the producing layer
                         TSTART
-                        // rendezvous of the two issuers: iteration 0 (accumulator overwrite) is issued, order the rest after it
-                        tc_fence_before();
-                        asm volatile("bar.sync 2, 64;\n" ::: "memory");
-                        tc_fence_after();
-                        TADD(tm_rdv)
+                        do {
+                            const int j = src - C.src_first;
+                            wait_ev(bar_act_ready(j), (act_cnt[j]++) & 1u);
+                            ++src;
+                            next_src_k = (src < src_end) ? (P.C[src].n0 >> 4) : 0x7fffffff;
+                        } while (s + nk - 1 >= next_src_k);
+                        TADD(tm_opnd)
                     }
-                    a_lo32 += static_cast<uint32_t>(2 * kps) * (KSTEP_BYTES >> 4);
-                    ta += 32u * static_cast<uint32_t>(kps);
-                    slot += two ? 2 : 1;
-                    if (slot >= nslots) {
-                        slot -= nslots;
+                    tc_fence_after();
+                    {
+                        TSTART
+                        if (elect_one()) {
+                            // up to 4 k-steps per slot, fully unrolled: the loop-invariant operands are moved to uniform registers once
+                            // per slot, not once per k-step (a rolled loop re-did 8 R2UR per k-step: ~125 issue cycles per k-step)
+                            const uint32_t bj = b_base32 + slot * slot16;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (j < nk && !(DBG & 1))
+                                    kstep_mma<FMT, PAIR>(ts, d, acur + j * astep, acur + j * astep + a2off, bj + j * kstep16, bj + j * kstep16 + b_lo16,
+                                                         desc_hi, idesc, (j > 0 || s > 0) ? 1u : 0u);
+                            }
+                            // the slot is freed -- in both CTAs of a pair -- by a commit behind the MMAs of its last k-step
+                            if (PAIR) mma2_commit_both(full + 8u * MAX_SLOTS);
+                            else mma_commit(full + 8u * MAX_SLOTS);
+                        }
+                        __syncwarp();
+                        TADD(tm_issue)
+                    }
+                    acur += astep * static_cast<uint32_t>(nk);
+                    if (++slot == nslots) {
+                        slot = 0;
                         rphase ^= 1u;
                     }
 #if VAE21_TC_TIMING
-                    if (mine) tm_it_mine += clock64() - t_it0; else tm_it_other += clock64() - t_it0;
+                    tm_iter += clock64() - t_it0;
 #endif
                 }
-                if (!PAIR || leader) {
-                    if (elect_one()) {
-                        if (PAIR) mma2_commit_both(bar_chunk_full(seq & (NFULL - 1)));
-                        else mma_commit(bar_chunk_full(seq & (NFULL - 1)));
-                        if (C.layer == 0 && C.last_in_layer) {  // the prologue warp(s) may overwrite a0 once these MMAs are done
-                            if (PAIR) mma2_commit_both(bar_a0_free);
-                            else mma_commit(bar_a0_free);
-                        }
+                if (elect_one()) {
+                    if (PAIR) mma2_commit_both(bar_chunk_full(seq & (NFULL - 1)));
+                    else mma_commit(bar_chunk_full(seq & (NFULL - 1)));
+                    if (C.layer == 0 && C.last_in_layer) {  // the prologue warp(s) may overwrite a0 once these MMAs are done
+                        if (PAIR) mma2_commit_both(bar_a0_free);
+                        else mma_commit(bar_a0_free);
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
                 ++seq;
             }
         }
 #if VAE21_TC_TIMING
-        if (mw == 0 && lane == 0 && blockIdx.x < 160) {
+        if (lane == 0 && blockIdx.x < 160) {
             long long* o = g_tc_timing[blockIdx.x];
             o[0] = clock64() - tm_total;
-            for (int i = 0; i < 5; ++i) { o[1 + i] = tm_evt[i]; o[6 + i] = tm_q[i]; }
-            o[11] = tm_ring; o[12] = tm_rdv; o[13] = tm_issue; o[14] = tm_setup; o[15] = tm_it_mine;
+            o[1] = tm_a0; o[2] = tm_q; o[3] = tm_ring; o[4] = tm_opnd; o[5] = tm_issue; o[6] = tm_iter;
         }
 #endif
-        }
-        __syncwarp();
-    } else if (warp == 3) {
-        // ===================== prologue warp: layer-0 operand of every tile ===================
-        // fused parameter transform (preprocess.py:74-78, :105-108) in fp32 -- the operand is split to 16-bit hi/lo pairs
-        // anyway -- -> a0 (k padded to 16).  Runs one tile ahead of the MMAs, off the epilogue warps' critical path
-        // (measured: the same work inside four epilogue warps cost 0.05 ms per 1M rows).
+    } else if (warp == 2 || warp == 3) {
+        // ===================== prologue warps: layer-0 operand of every tile ===================
+        // fused parameter transform (preprocess.py:74-78, :105-108) -> a0 (k padded to 16); role 2 takes rows 0..63, role 3 rows
+        // 64..127.  They run one tile ahead of the MMAs, off the epilogue warps' critical path.
         const int K0 = P.K0;
         uint32_t nfree = 0;
+#pragma unroll 1
         for (long long unit = unit0; unit < nunits; unit += ustep, ++nfree) {
             const long long tile = CG * unit + rank;
             if (nfree > 0) mbar_wait(bar_a0_free, (nfree - 1u) & 1u);
-            for (int rr = 0; rr < MT / 32; ++rr) {
-                const int row = rr * 32 + lane;
-                const long long grow = tile * MT + row;
+#pragma unroll 1
+            for (int rr = 0; rr < MT / 64; ++rr) {
+                const int row = (warp - 2) * (MT / 2) + rr * 32 + lane;
                 float x[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) x[j] = 0.f;
-                if (DBG & 256) {
-                } else if (grow < a.n && a.in_mode == IN_GRID) {
-                    grid_point(a, static_cast<unsigned long long>(a.row_base + grow), K0, x);
-                } else if (grow < a.n) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (j < K0) {
-                            const long long g = grow * K0 + j;
-                            if (a.in_mode == IN_NORMALISED_F32) {
-                                x[j] = reinterpret_cast<const float*>(a.in)[g];
-                            } else {
-                                const double pd = (a.in_mode == IN_PARAMS_F64)
-                                                      ? reinterpret_cast<const double*>(a.in)[g]
-                                                      : static_cast<double>(reinterpret_cast<const float*>(a.in)[g]);
-                                float pf = static_cast<float>(pd);
-                                if (j == nc.floor_col && pd == 0.0) pf = static_cast<float>(nc.floor_val);
-                                float t = pf;
-                                if (nc.log_mask[j]) {
-                                    t = log10f(pf);
-                                    // a finite non-zero double outside the float range: take the slow exact route
-                                    if ((pf == 0.f || isinf(pf)) && pd != 0.0 && !isinf(pd)) t = static_cast<float>(log10(pd));
-                                }
-                                x[j] = fmaf(t - s_pmin[j], s_pscale[j], -1.f);
-                            }
-                        }
-                    }
-                }
+                prologue_row(a, nc, tile * MT + row, K0, x);
                 uint32_t w[16];
                 split16<FMT>(x, w);
                 uint8_t* a0 = sm + P.off_a0;
@@ -1180,17 +1113,16 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
-                if (PAIR && !leader && VAE21_TC_DIRECT_ARRIVE == 1) mbar_arrive_remote(bar_a0_ready, 0);
-                else if (PAIR && !leader && VAE21_TC_DIRECT_ARRIVE == 2) mbar_arrive_remote_release(bar_a0_ready, 0);
+                if (PAIR && !leader) mbar_arrive_remote(bar_a0_ready, 0);
                 else mbar_arrive(bar_a0_ready);
             }
         }
     } else if (warp >= 4) {
         // ===================== epilogue warps ================================================
-        // thread = tile row = TMEM lane; the two warps that share a TMEM sub-partition split the
-        // 16-column groups of every accumulator chunk (even / odd groups).
+        // thread = tile row = TMEM lane; the EPS warps that share a TMEM sub-partition split the 16-column groups of every
+        // accumulator chunk (group g goes to warp share g mod EPS).
         const int ew = warp - 4;
-        const int half = ew >> 2;                 // which share of the 16-column groups (0 also does the prologue)
+        const int half = ew >> 2;                 // which share of the 16-column groups
         const int sub = warp & 3;                 // TMEM sub-partition this warp may access
         const int row = sub * 32 + lane;          // tile row == TMEM lane
         const uint32_t tlane = static_cast<uint32_t>(sub * 32) << 16;
@@ -1198,27 +1130,27 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         const int NO = P.n_out;
         uint32_t seq = 0;
         uint32_t tcount = 0;
+        float vmax = 0.f;  // largest hidden activation this thread converted (operand-range check, FMT 1 / 2)
 
         // hand-off to the MMA issuer, which lives in the leader CTA of a pair
         auto signal_mma = [&](uint32_t bar) {
-            if (PAIR && !leader && VAE21_TC_DIRECT_ARRIVE == 1) mbar_arrive_remote(bar, 0);
-            else if (PAIR && !leader && VAE21_TC_DIRECT_ARRIVE == 2) mbar_arrive_remote_release(bar, 0);
+            if (PAIR && !leader) mbar_arrive_remote(bar, 0);
             else mbar_arrive(bar);
         };
 
+#pragma unroll 1
         for (long long unit = unit0; unit < nunits; unit += ustep, ++tcount) {
             const long long tile = CG * unit + rank;
             const long long grow = tile * MT + row;
             const bool full_tile = (tile * MT + MT <= a.n);
-            // output pointer of (row 32*sub + lane/16, column lane%16): each store instruction of the final layer
-            // writes two 64-byte row segments
+            // OM_ROWS: every store instruction of the final layer writes two 64-byte row segments -- lanes 0..15 the 16 columns of
+            // staged row R, lanes 16..31 those of row R + 4 (20-float staging rows: 4 rows apart = 16 banks apart, conflict-free)
             const int cl = lane & 15, rsel = lane >> 4;
-            float* orow = a.out + (tile * MT + sub * 32 + rsel) * static_cast<long long>(NO) + cl;
+            const long long orow0 = tile * MT + sub * 32 + 4 * rsel;
             float chi = 0.f, amp = 0.f;
+#pragma unroll 1
             for (int c = 0; c < n_chunks; ++c) {
-                // The chunk record is read BEFORE the wait: the (dynamically indexed) constant loads then overlap the wait instead
-                // of sitting, one dependent ~100-cycle load after the other, on the critical path behind it (the wait's inline
-                // assembly is a compiler barrier, so loads placed after it are issued after it).
+                // The chunk record is read BEFORE the wait: the (dynamically indexed) constant loads then overlap the wait.
                 const Chunk& C = P.C[c];
                 const int c_bias_n0 = C.bias_n0, c_ncols = C.ncols, c_dcol = C.dcol, c_n0 = C.n0, c_qbuf = C.qbuf, c_idx = C.idx_in_layer;
                 const int out_dst = C.out_dst;
@@ -1230,11 +1162,11 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 const float* bl = s_bias + c_bias_n0;
                 const int ng = c_ncols / 16;
                 const uint32_t tbase = tm + tlane + static_cast<uint32_t>(c_dcol);
+                // group body (instantiated twice: the accumulator reads are software-pipelined over two register sets, so the load of
+                // this warp's next group is in flight while the current one is converted)
                 auto process = [&](uint32_t (&r)[16], int g) {
-                    const uint32_t taddr = tbase + static_cast<uint32_t>(16 * g);
-                    if (out_dst != DST_FINAL) {
-                        uint32_t w[16];  // [0..7] hi words, [8..15] second-tile words (see split16)
-                        float v[16];
+                    float v[16];
+                        if (out_dst != DST_FINAL) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float4 b4 = *reinterpret_cast<const float4*>(bl + 16 * g + 4 * q);
@@ -1249,34 +1181,10 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                                 v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
                                 v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
                             }
-                            if (do_relu) {
-                                v[4 * q + 0] = relu_nan(v[4 * q + 0]);
-                                v[4 * q + 1] = relu_nan(v[4 * q + 1]);
-                                v[4 * q + 2] = relu_nan(v[4 * q + 2]);
-                                v[4 * q + 3] = relu_nan(v[4 * q + 3]);
-                            }
-                        }
-                        if (DBG & 16) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) w[i] = __float_as_uint(v[i]);
-                        } else {
-                            split16<FMT>(v, w);
-                        }
-                        if (DBG & 32) {
-                            if (w[3] == 0x12345u) tmem_st16(taddr, w);
-                        } else if (out_dst == DST_TMEM) {
-                            tmem_st16(taddr, w);  // in place: these 16 columns become the next layer's k-step
-                        } else {
-                            uint8_t* dst = sm + P.off_act + ((c_n0 >> 4) + g) * KSTEP_BYTES + row * 16;
-                            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-                            *reinterpret_cast<uint4*>(dst + A_KG_BYTES) = make_uint4(w[4], w[5], w[6], w[7]);
-                            *reinterpret_cast<uint4*>(dst + 2 * A_KG_BYTES) = make_uint4(w[8], w[9], w[10], w[11]);
-                            *reinterpret_cast<uint4*>(dst + 3 * A_KG_BYTES) = make_uint4(w[12], w[13], w[14], w[15]);
                         }
                     } else {
                         const int n = c_n0 + 16 * g;
                         const float s1 = ((a.out_mode == OUT_NORMALISED) ? 1.f : nc.sd) * inv_s8;
-                        float v[16];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float4 s4 = *reinterpret_cast<const float4*>(s_s0 + n + 4 * q);
@@ -1285,57 +1193,81 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                             v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), s1, s4.z);
                             v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), s1, s4.w);
                         }
-                        if (a.out_mode == OUT_CHI2) {
+                    }
+                    if (out_dst != DST_FINAL) {
+                        if (do_relu) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const float rr = (v[i] - s_obs[n + i]) * s_isig[n + i];  // isig = 0 on padding
-                                chi = fmaf(rr, rr, chi);
-                            }
-                        } else if (a.out_mode == OUT_ERROR) {
-                            // emulator.py:185-191 fused: squared difference to this row's true signal and its amplitude, in the band
-                            const float* tr = a.truth + grow * static_cast<long long>(NO) + n;
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const float t = (grow < a.n && n + i < NO) ? __ldg(tr + i) : 0.f;
-                                const float rr = (v[i] - t) * s_isig[n + i];
-                                chi = fmaf(rr, rr, chi);
-                                amp = fmaxf(amp, fabsf(t) * s_isig[n + i]);
-                            }
-                        } else if (DBG & 8) {
-                            if (v[3] == 12345.f) a.out[0] = v[0];
-                        } else {
-                            // 32x16 transpose through this warp's staging tile (row stride 20 floats: conflict-free
-                            // 128-bit writes) -> every store instruction writes two 64-byte row segments
-                            float4* st4 = reinterpret_cast<float4*>(stage + lane * 20);
-                            st4[0] = make_float4(v[0], v[1], v[2], v[3]);
-                            st4[1] = make_float4(v[4], v[5], v[6], v[7]);
-                            st4[2] = make_float4(v[8], v[9], v[10], v[11]);
-                            st4[3] = make_float4(v[12], v[13], v[14], v[15]);
-                            __syncwarp();
-                            const float* sp = stage + rsel * 20 + cl;
-                            float* op = orow + n;
-                            if (full_tile && n + 16 <= NO && NO == 451) {
-                                // the reference's 451-bin grid: row offsets are immediates of the store instructions
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) __stcs(op + 2 * i * 451, sp[2 * i * 20]);
-                            } else if (full_tile && n + 16 <= NO) {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) __stcs(op + static_cast<long long>(2 * i) * NO, sp[2 * i * 20]);
-                            } else {
-                                const long long rbase = tile * MT + sub * 32 + rsel;
-#pragma unroll
-                                for (int i = 0; i < 16; ++i)
-                                    if (rbase + 2 * i < a.n && n + cl < NO) __stcs(op + static_cast<long long>(2 * i) * NO, sp[2 * i * 20]);
-                            }
-                            __syncwarp();
+                            for (int i = 0; i < 16; ++i) v[i] = relu_nan(v[i]);
                         }
+                        if (FMT != 0) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 2) vmax = fmax3_abs(vmax, v[i], v[i + 1]);
+                        }
+                        uint32_t w[16];  // [0..7] hi words, [8..15] second-tile words (see split16)
+                        if (DBG & 16) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) w[i] = __float_as_uint(v[i]);
+                        } else {
+                            split16<FMT>(v, w);
+                        }
+                        if (out_dst == DST_TMEM) {
+                            tmem_st16(tbase + static_cast<uint32_t>(16 * g), w);  // in place: these 16 columns become the next layer's k-step
+                        } else {
+                            uint8_t* dst = sm + P.off_act + ((c_n0 >> 4) + g) * KSTEP_BYTES + row * 16;
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                            *reinterpret_cast<uint4*>(dst + A_KG_BYTES) = make_uint4(w[4], w[5], w[6], w[7]);
+                            *reinterpret_cast<uint4*>(dst + 2 * A_KG_BYTES) = make_uint4(w[8], w[9], w[10], w[11]);
+                            *reinterpret_cast<uint4*>(dst + 3 * A_KG_BYTES) = make_uint4(w[12], w[13], w[14], w[15]);
+                        }
+                    } else if (OM == OM_CHI2) {
+                        const int n = c_n0 + 16 * g;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float rr = (v[i] - s_obs[n + i]) * s_isig[n + i];  // isig = 0 on padding
+                            chi = fmaf(rr, rr, chi);
+                        }
+                    } else if (OM == OM_ERROR) {
+                        // emulator.py:185-191 fused: squared difference to this row's true signal and its amplitude, in the band
+                        const int n = c_n0 + 16 * g;
+                        const float* tr = a.truth + grow * static_cast<long long>(NO) + n;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float t = (grow < a.n && n + i < NO) ? __ldg(tr + i) : 0.f;
+                            const float rr = (v[i] - t) * s_isig[n + i];
+                            chi = fmaf(rr, rr, chi);
+                            amp = fmaxf(amp, fabsf(t) * s_isig[n + i]);
+                        }
+                    } else if (!(DBG & 8)) {
+                        // 32x16 transpose through this warp's staging tile (row stride 20 floats: conflict-free 128-bit writes)
+                        const int n = c_n0 + 16 * g;
+                        float4* st4 = reinterpret_cast<float4*>(stage + lane * 20);
+                        st4[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        st4[1] = make_float4(v[4], v[5], v[6], v[7]);
+                        st4[2] = make_float4(v[8], v[9], v[10], v[11]);
+                        st4[3] = make_float4(v[12], v[13], v[14], v[15]);
+                        __syncwarp();
+                        const float* sp = stage + (4 * rsel) * 20 + cl;
+                        float* op = a.out + orow0 * static_cast<long long>(NO) + n + cl;
+                        if (full_tile && n + 16 <= NO) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {  // staged rows R = (i & 3) + 8 (i >> 2) and R + 4
+                                const int R = (i & 3) + 8 * (i >> 2);
+                                __stcs(op + static_cast<long long>(R) * NO, sp[R * 20]);
+                            }
+                        } else {
+#pragma unroll 1
+                            for (int i = 0; i < 16; ++i) {
+                                const int R = (i & 3) + 8 * (i >> 2);
+                                if (orow0 + R < a.n && n + cl < NO) __stcs(op + static_cast<long long>(R) * NO, sp[R * 20]);
+                            }
+                        }
+                        __syncwarp();
                     }
                 };
-                // software-pipelined accumulator reads: the load of this warp's next group is in flight while
-                // the current one is converted
                 if (half < ng && !(DBG & 2)) {
                     uint32_t ra[16], rb[16];
                     tmem_ld16(tbase + static_cast<uint32_t>(16 * half), ra);
+#pragma unroll 1
                     for (int g = half; g < ng; g += 2 * EPS) {
                         tmem_ld_wait();
                         if (g + EPS < ng) tmem_ld16(tbase + static_cast<uint32_t>(16 * (g + EPS)), rb);
@@ -1358,13 +1290,13 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 }
             }
             // tile end: all epilogue warps meet (the output staging tiles alias the activation buffer, and the
-            // two column halves of a row combine their chi^2 partials here)
+            // column shares of a row combine their chi^2 partials here)
             float* chi_buf = s_chi + (tcount & 1u) * (EPS - 1) * 128;
             float* amp_buf = s_amp + (tcount & 1u) * (EPS - 1) * 128;
-            if ((a.out_mode == OUT_CHI2 || a.out_mode == OUT_ERROR) && half > 0) chi_buf[(half - 1) * 128 + row] = chi;
-            if (a.out_mode == OUT_ERROR && half > 0) amp_buf[(half - 1) * 128 + row] = amp;
+            if ((OM == OM_CHI2 || OM == OM_ERROR) && half > 0) chi_buf[(half - 1) * 128 + row] = chi;
+            if (OM == OM_ERROR && half > 0) amp_buf[(half - 1) * 128 + row] = amp;
             asm volatile("bar.sync 1, %0;\n" ::"n"(NEPI) : "memory");
-            if (a.out_mode == OUT_ERROR && half == 0) {
+            if (OM == OM_ERROR && half == 0) {
 #pragma unroll
                 for (int hh = 0; hh < EPS - 1; ++hh) {
                     chi += chi_buf[hh * 128 + row];
@@ -1376,7 +1308,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                     a.chi2[grow] = e;
                 }
             }
-            if (a.out_mode == OUT_CHI2 && half == 0) {
+            if (OM == OM_CHI2 && half == 0) {
 #pragma unroll
                 for (int hh = 0; hh < EPS - 1; ++hh) chi += chi_buf[hh * 128 + row];
                 unsigned long long key = ~0ull;
@@ -1394,6 +1326,13 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 }
             }
         }
+        // operand-range check (FMT 1: fp16 hi/lo overflow beyond 65504; FMT 2: the e4m3 correction operands clip at 448): count the
+        // epilogue threads that converted a hidden activation beyond the range.  fmaxf ignores NaN, so the reference's NaN
+        // propagation for non-positive parameters does not count.
+        if (FMT != 0 && a.sat) {
+            const unsigned m = __ballot_sync(0xffffffffu, vmax > sat_limit<FMT>());
+            if (lane == 0 && m) atomicAdd(a.sat, static_cast<unsigned long long>(__popc(m)));
+        }
     }
 
     // ---- teardown -------------------------------------------------------------------------
@@ -1407,9 +1346,17 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     }
 }
 
-template <int FMT, int CG>
+template <int FMT, int CG, int OM>
 inline cudaError_t launch_one(const Plan& P, const NormConsts& nc, const LaunchArgs& a, const uint8_t* wimg, const float* bias,
                               int grid, cudaStream_t st) {
+    static unsigned long long prepared = 0;  // per instantiation: bit d = the shared-memory attribute is set on device d
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64 || !((prepared >> dev) & 1ull)) {
+        cudaError_t e = cudaFuncSetAttribute(vae21_tc_kernel<FMT, CG, OM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e != cudaSuccess) return e;
+        if (dev < 64) prepared |= 1ull << dev;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(NTHREADS);
@@ -1422,17 +1369,17 @@ inline cudaError_t launch_one(const Plan& P, const NormConsts& nc, const LaunchA
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, vae21_tc_kernel<FMT, CG>, P, nc, a, wimg, bias);
+    return cudaLaunchKernelEx(&cfg, vae21_tc_kernel<FMT, CG, OM>, P, nc, a, wimg, bias);
 }
 
-inline cudaError_t prepare() {
-    cudaError_t e;
-    if ((e = cudaFuncSetAttribute(vae21_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(vae21_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(vae21_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(vae21_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(vae21_tc_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(vae21_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+inline cudaError_t prepare() { return cudaSuccess; }  // attributes are set per instantiation on first launch (launch_one)
+
+template <int FMT, int CG>
+inline cudaError_t launch_om(const Plan& P, const NormConsts& nc, const LaunchArgs& a, const uint8_t* w, const float* bias, int grid,
+                             cudaStream_t st) {
+    if (a.out_mode == OUT_CHI2) return launch_one<FMT, CG, OM_CHI2>(P, nc, a, w, bias, grid, st);
+    if (a.out_mode == OUT_ERROR) return launch_one<FMT, CG, OM_ERROR>(P, nc, a, w, bias, grid, st);
+    return launch_one<FMT, CG, OM_ROWS>(P, nc, a, w, bias, grid, st);
 }
 
 // cta_group: 1 = one CTA per 128-row tile, 2 = CTA pairs on 256-row super-tiles
@@ -1445,13 +1392,13 @@ inline cudaError_t launch(const Plan& P, const NormConsts& nc, const LaunchArgs&
     if (cg == 2) {
         const long long nunits = (a.n + 2 * MT - 1) / (2 * MT);
         const int grid = 2 * static_cast<int>(std::min<long long>(nunits, sm_count / 2));
-        return fmt == 0 ? launch_one<0, 2>(P, nc, a, w, bias, grid, st)
-               : fmt == 1 ? launch_one<1, 2>(P, nc, a, w, bias, grid, st) : launch_one<2, 2>(P, nc, a, w, bias, grid, st);
+        return fmt == 0 ? launch_om<0, 2>(P, nc, a, w, bias, grid, st)
+               : fmt == 1 ? launch_om<1, 2>(P, nc, a, w, bias, grid, st) : launch_om<2, 2>(P, nc, a, w, bias, grid, st);
     }
     const long long ntiles = (a.n + MT - 1) / MT;
     const int grid = static_cast<int>(std::min<long long>(ntiles, sm_count));
-    return fmt == 0 ? launch_one<0, 1>(P, nc, a, w, bias, grid, st)
-           : fmt == 1 ? launch_one<1, 1>(P, nc, a, w, bias, grid, st) : launch_one<2, 1>(P, nc, a, w, bias, grid, st);
+    return fmt == 0 ? launch_om<0, 1>(P, nc, a, w, bias, grid, st)
+           : fmt == 1 ? launch_om<1, 1>(P, nc, a, w, bias, grid, st) : launch_om<2, 1>(P, nc, a, w, bias, grid, st);
 }
 
 #if VAE21_TC_TIMING

@@ -119,6 +119,8 @@ struct vae21_handle {
     float* d_mu = nullptr;
     float* d_obs = nullptr;
     float* d_isig = nullptr;
+    float* d_mask = nullptr;  // band mask of vae21_error (its own buffer: d_isig keeps the cached observation)
+    int alloc_out = 0;        // output width d_mu / d_obs / d_isig / d_mask are allocated for
     unsigned long long* d_key = nullptr;
     // host copies of what d_obs / d_isig hold: an MCMC or grid loop passes the same observation on every call, and two small
     // pageable-memory uploads per call are a visible part of a 45-microsecond launch
@@ -130,6 +132,11 @@ struct vae21_handle {
     float* d_out[NSLOT] = {nullptr, nullptr, nullptr};
     size_t cap_in[NSLOT] = {0, 0, 0}, cap_out[NSLOT] = {0, 0, 0};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // ordering against the caller's stream: `ev_in` marks "the caller's device buffers are ready" for the pipeline streams,
+    // `ev_use` the last kernel launched on a caller's stream (it reads d_mu / d_obs / d_isig / the weight images)
+    cudaEvent_t ev_in = nullptr, ev_use = nullptr;
+    bool use_pending = false;
+    unsigned long long* d_sat = nullptr;  // [2] saturation counters of the tensor-core operand conversion (see vae21_get_info)
     long long launches = 0;
     float last_ms = -1.f;
 };
@@ -138,6 +145,16 @@ namespace {
 
 int use_device(vae21_handle* h) {
     CK(cudaSetDevice(h->device));
+    return 0;
+}
+
+// A kernel launched asynchronously on a caller's stream may still be reading the handle's constants (d_mu, d_obs, d_isig, d_mask,
+// weight images): wait for it before any of them is rewritten.
+int wait_last_use(vae21_handle* h) {
+    if (h->use_pending) {
+        CK(cudaEventSynchronize(h->ev_use));
+        h->use_pending = false;
+    }
     return 0;
 }
 
@@ -241,7 +258,9 @@ int launch(vae21_handle* h, const LaunchArgs& a, int precision, cudaStream_t st)
         if (!h->tc_ok)
             return fail(VAE21_ERR_UNSUPPORTED, "tensor-core path unavailable for this layer stack: %s", h->tc_why.c_str());
         const int fmt = precision == VAE21_TC_FP16X3 ? 1 : precision == VAE21_TC_FP16E4M3 ? 2 : 0;
-        cudaError_t e = tck::launch(h->tc, h->nc, a, h->d_wtc[fmt], h->d_btc, fmt, h->sm_count, st);
+        LaunchArgs at = a;
+        at.sat = h->d_sat;
+        cudaError_t e = tck::launch(h->tc, h->nc, at, h->d_wtc[fmt], h->d_btc, fmt, h->sm_count, st);
         if (e != cudaSuccess) return fail(VAE21_ERR_CUDA, "tensor-core kernel launch failed: %s", cudaGetErrorString(e));
         h->launches++;
         return 0;
@@ -255,6 +274,7 @@ int upload_observation(vae21_handle* h, const float* obs, const float* isig, int
         std::memcmp(h->h_isig.data(), isig, sizeof(float) * NO) == 0)
         return 0;
     h->obs_cached = false;
+    if (int rc = wait_last_use(h)) return rc;
     h->h_obs.assign(obs, obs + NO);
     h->h_isig.assign(isig, isig + NO);
     CK(cudaMemcpyAsync(h->d_obs, h->h_obs.data(), sizeof(float) * NO, cudaMemcpyHostToDevice, st));
@@ -308,7 +328,16 @@ int run(vae21_handle* h, const void* in, int in_mode, bool in_dev, long long n, 
             a.n = n;
             a.row_base = 0;
             if (int rc = launch(h, a, precision, ust)) return rc;
+            CK(cudaEventRecord(h->ev_use, ust));
+            h->use_pending = true;
         } else {
+            // A device-resident input (or output) belongs to the caller's stream: the pipeline streams must not touch it before
+            // the work already queued there has finished.  (The call returns only after the pipeline streams have drained, so
+            // nothing the caller queues afterwards can overtake it.)
+            if (in_dev || out_dev) {
+                CK(cudaEventRecord(h->ev_in, ust));
+                for (int s = 0; s < NSLOT; ++s) CK(cudaStreamWaitEvent(h->streams[s], h->ev_in, 0));
+            }
             const size_t out_row = chi ? sizeof(float) : sizeof(float) * NO;
             const long long chunk = chi ? CHUNK_ROWS * 16 : CHUNK_ROWS;
             long long done = 0;
@@ -399,7 +428,10 @@ int vae21_create(int device, vae21_handle** out) {
         }
     }
     if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
-        cudaMalloc(&h->d_key, sizeof(unsigned long long)) != cudaSuccess) {
+        cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_use, cudaEventDisableTiming) != cudaSuccess ||
+        cudaMalloc(&h->d_key, sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&h->d_sat, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(h->d_sat, 0, 2 * sizeof(unsigned long long)) != cudaSuccess) {
         vae21_destroy(h);
         return fail(VAE21_ERR_CUDA, "handle resource creation failed");
     }
@@ -420,7 +452,12 @@ int vae21_destroy(vae21_handle* h) {
     }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    void* ptrs[] = {h->d_w32, h->d_b32, h->d_wtc[0], h->d_wtc[1], h->d_wtc[2], h->d_btc, h->d_mu, h->d_obs, h->d_isig, h->d_key};
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_use) {
+        cudaEventSynchronize(h->ev_use);
+        cudaEventDestroy(h->ev_use);
+    }
+    void* ptrs[] = {h->d_w32, h->d_b32, h->d_wtc[0], h->d_wtc[1], h->d_wtc[2], h->d_btc, h->d_mu, h->d_obs, h->d_isig, h->d_mask, h->d_key, h->d_sat};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete h;
@@ -438,10 +475,23 @@ int vae21_set_model(vae21_handle* h, int n_layers, const int* dims, const float*
         if (!kernels[l] || !biases[l]) return fail(VAE21_ERR_ARG, "null kernel/bias for layer %d", l);
     if (int rc = use_device(h)) return rc;
     for (int s = 0; s < NSLOT; ++s) CK(cudaStreamSynchronize(h->streams[s]));
+    if (int rc = wait_last_use(h)) return rc;  // weight images are about to be replaced
     h->model_set = false;
-    const int old_out = h->n_layers ? h->dims[h->n_layers] : -1;
+    const int old_in = h->n_layers ? h->dims[0] : -1;
     h->n_layers = n_layers;
     for (int l = 0; l <= n_layers; ++l) h->dims[l] = dims[l];
+    // a failure below leaves model_set == false (every compute call refuses) and n_layers == 0, so a retry starts from scratch
+    struct Rollback {
+        vae21_handle* h;
+        bool ok = false;
+        ~Rollback() {
+            if (!ok) {
+                h->n_layers = 0;
+                h->tc_ok = false;
+                h->norm_set = false;
+            }
+        }
+    } guard{h};
     if (int rc = pack_fp32(h, kernels, biases, relu_flags)) return rc;
     // tensor-core plan (optional: a stack that does not fit leaves the fp32 path usable)
     h->tc_ok = false;
@@ -468,16 +518,20 @@ int vae21_set_model(vae21_handle* h, int n_layers, const int* dims, const float*
         }
     }
     const int NO = dims[n_layers];
-    if (NO != old_out) {
+    if (NO != h->alloc_out) {  // the width the constant buffers are ALLOCATED for, not what an earlier (possibly failed) call recorded
         h->obs_cached = false;
         h->norm_set = false;
-        for (float** p : {&h->d_mu, &h->d_obs, &h->d_isig}) {
+        h->alloc_out = 0;
+        for (float** p : {&h->d_mu, &h->d_obs, &h->d_isig, &h->d_mask}) {
             if (*p) cudaFree(*p);
             *p = nullptr;
             CK(cudaMalloc(p, sizeof(float) * NO));
             CK(cudaMemset(*p, 0, sizeof(float) * NO));
         }
+        h->alloc_out = NO;
     }
+    if (dims[0] != old_in) h->norm_set = false;  // the prologue constants were for another input width
+    guard.ok = true;
     h->model_set = true;
     return 0;
 }
@@ -496,11 +550,13 @@ int vae21_set_norm(vae21_handle* h, int n_par, const double* par_min, const doub
         nc.pmin[j] = par_min[j];
         nc.prange[j] = par_max[j] - par_min[j];  // same fp64 subtraction numpy performs (preprocess.py:106)
         nc.log_mask[j] = log_mask[j] ? 1 : 0;
+        nc.pscale[j] = 2.0 / nc.prange[j];
     }
     nc.floor_col = floor_col;
     nc.floor_val = fx_floor;
     nc.sd = sig_std;
     for (int s = 0; s < NSLOT; ++s) CK(cudaStreamSynchronize(h->streams[s]));
+    if (int rc = wait_last_use(h)) return rc;
     CK(cudaMemcpy(h->d_mu, sig_mean, sizeof(float) * n_out, cudaMemcpyHostToDevice));
     h->norm_set = true;
     return 0;
@@ -572,8 +628,11 @@ int vae21_chi2_grid(vae21_handle* h, int n_dim, const int* npts, const double* x
         a.grid_lo[j] = static_cast<float>(x_lo[j]);
         a.grid_step[j] = npts[j] > 1 ? static_cast<float>((x_hi[j] - x_lo[j]) / (npts[j] - 1)) : 0.f;
     }
-    if (count > 0)
+    if (count > 0) {
         if (int rc = launch(h, a, precision, st)) return rc;
+        CK(cudaEventRecord(h->ev_use, st));
+        h->use_pending = true;
+    }
     if (want_best) {
         unsigned long long key = ~0ull;
         CK(cudaMemcpyAsync(&key, h->d_key, sizeof key, cudaMemcpyDeviceToHost, st));
@@ -611,8 +670,8 @@ int vae21_error(vae21_handle* h, const void* params, int params_dtype, int param
         }
     }
     if (in_band == 0) return fail(VAE21_ERR_ARG, "the frequency band contains no bin");
-    h->obs_cached = false;  // d_isig is about to hold the band mask
-    CK(cudaMemcpyAsync(h->d_isig, mask.data(), sizeof(float) * NO, cudaMemcpyHostToDevice, st));
+    if (int rc = wait_last_use(h)) return rc;  // an earlier asynchronous error launch may still read the mask
+    CK(cudaMemcpyAsync(h->d_mask, mask.data(), sizeof(float) * NO, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));  // `mask` goes out of scope
     void *d_par = nullptr, *d_truth = nullptr, *d_err = nullptr;
     auto cleanup = [&]() {
@@ -639,7 +698,7 @@ int vae21_error(vae21_handle* h, const void* params, int params_dtype, int param
     }
     a.mu = h->d_mu;
     a.obs = h->d_obs;
-    a.isig = h->d_isig;
+    a.isig = h->d_mask;  // the band mask travels in the inv_sigma slot
     a.in_mode = params_dtype == VAE21_F64 ? IN_PARAMS_F64 : IN_PARAMS_F32;
     a.out_mode = OUT_ERROR;
     a.n = n;
@@ -659,6 +718,17 @@ int vae21_get_info(vae21_handle* h, int64_t* kernel_launches, float* last_kernel
     if (kernel_launches) *kernel_launches = h->launches;
     if (last_kernel_ms) *last_kernel_ms = h->last_ms;
     if (tc_supported) *tc_supported = h->tc_ok ? 1 : 0;
+    return 0;
+}
+
+int vae21_get_tc_stats(vae21_handle* h, int64_t* saturated, int reset) {
+    if (!h) return fail(VAE21_ERR_ARG, "null handle");
+    if (int rc = use_device(h)) return rc;
+    unsigned long long v[2] = {0, 0};
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(v, h->d_sat, sizeof v, cudaMemcpyDeviceToHost));
+    if (saturated) *saturated = static_cast<int64_t>(v[0]);
+    if (reset) CK(cudaMemset(h->d_sat, 0, sizeof v));
     return 0;
 }
 
@@ -686,6 +756,7 @@ int vae21_time_predict(vae21_handle* h, const void* params_dev, int params_dtype
 #if VAE21_TC_TIMING
 // profiling builds only (not declared in vae21.h)
 int vae21_debug_tc_timing(long long* out) { return tck::read_timing(out) == cudaSuccess ? 0 : 3; }
+
 #endif
 
 }  // extern "C"

@@ -261,23 +261,9 @@ class DirectEmulator:
     def __init__(self, par_train=None, par_val=None, par_test=None, signal_train=None, signal_val=None,
                  signal_test=None, hidden_dims=hidden_dims, activation_func="relu", redshifts=redshifts,
                  frequencies=None, *, stats: Optional[pp.NormStats] = None, device: int = 0, precision=None):
-        if par_train is None and signal_train is None and stats is None:
-            ds_path = os.environ.get(DATASET_ENV) or (PATH + "dataset_21cmVAE.h5")
-            if os.path.isfile(ds_path):
-                d = _load_dataset(ds_path)
-                par_train, par_val, par_test = d["par_train"], d["par_val"], d["par_test"]
-                signal_train, signal_val, signal_test = d["signal_train"], d["signal_val"], d["signal_test"]
-            else:
-                raise IOError(
-                    "no training set: pass par_train/signal_train (or stats=NormStats), or point "
-                    f"{DATASET_ENV} at dataset_21cmVAE.h5 (nothing is downloaded at import, unlike the reference)")
-        self.par_train, self.par_val, self.par_test = par_train, par_val, par_test
-        self.signal_train, self.signal_val, self.signal_test = signal_train, signal_val, signal_test
+        (self.par_train, self.par_val, self.par_test, self.signal_train, self.signal_val, self.signal_test,
+         stats) = _resolve_training_set(par_train, par_val, par_test, signal_train, signal_val, signal_test, stats)
         self.par_labels = ["fstar", "Vc", "fx", "tau", "alpha", "nu_min", "Rmfp"]
-        if stats is None:
-            if par_train is None or signal_train is None:
-                raise ValueError("both par_train and signal_train are needed to compute the normalisation constants")
-            stats = pp.NormStats.from_training_set(par_train, signal_train)
         self.stats = stats
         self.device = int(device)
         self.precision = precision
@@ -316,8 +302,9 @@ class DirectEmulator:
 
         ``callbacks`` are objects of ``training.EarlyStopping`` / ``training.ReduceLROnPlateau`` (same constructor
         arguments as the tf.keras callbacks of notebooks/Training.ipynb; TensorFlow objects are not accepted -- there is no
-        TensorFlow here).  The optimiser comes from ``self.emulator.compile(optimizer=training.Adam(0.01), loss=...)``;
-        without ``compile`` Adam with the Keras default learning rate 1e-3 is used.  ``verbose="tqdm"`` maps to one line per
+        TensorFlow here).  The model must have been compiled, as in the reference's notebooks:
+        ``self.emulator.compile(optimizer=training.Adam(0.01), loss=relative_mse_loss(signal_train))``; an uncompiled model,
+        another loss or a non-Adam optimiser raises (Keras would train them; this trainer cannot).  ``verbose="tqdm"`` maps to one line per
         epoch.  Extra keywords: ``seed`` fixes the shuffling, ``distributed=True`` splits every batch over the ranks of an
         initialised torch.distributed group (gradient all-reduce over NCCL).
 
@@ -335,15 +322,20 @@ class DirectEmulator:
             x_val = pp.par_transform(self.par_val, self.par_train).astype(np.float32)
             y_val = pp.preproc(np.asarray(self.signal_val), self.signal_train).astype(np.float32)
             w_val = amp_w(y_val)
-        compiled = self.emulator._compiled or {}
+        # Keras refuses to fit a model that was never compiled, and trains whatever loss / optimiser compile() was given.
+        # This trainer implements exactly one configuration -- Adam on the relative-MSE loss (notebooks/Training.ipynb cell 4) --
+        # so anything else is an error here, never a silent substitution.
+        compiled = self.emulator._compiled
+        if compiled is None:
+            raise RuntimeError("You must compile your model before training/testing. Use `emulator.compile(optimizer, loss)` "
+                               "with optimizer=training.Adam(lr) and loss=relative_mse_loss(signal_train).")
+        loss = compiled.get("loss")
+        if loss is not None and getattr(loss, "__name__", None) != "loss_function":
+            raise ValueError(f"unsupported loss {loss!r}: the CUDA trainer implements relative_mse_loss(signal_train) "
+                             "(emulator.py:51-83) only; pass that (or loss=None for the same objective)")
         opt = compiled.get("optimizer")
-        if opt is None:
-            opt = tr.Adam()
-        elif not isinstance(opt, tr.Adam):
-            lr = getattr(opt, "learning_rate", getattr(opt, "lr", None))
-            if lr is None:
-                raise TypeError("optimizer must be training.Adam or expose .learning_rate")
-            opt = tr.Adam(float(lr))
+        if not isinstance(opt, tr.Adam):
+            raise TypeError(f"unsupported optimizer {opt!r}: pass training.Adam(learning_rate, beta_1, beta_2, epsilon)")
         w = self.emulator.weights
         flat, hist = tr.fit(w.dims, w.relu, tr.flatten_weights(w.kernels, w.biases), x_train, y_train, amp_w(y_train), x_val, y_val,
                             w_val, optimizer=opt, epochs=epochs, batch_size=256, callbacks=list(callbacks), seed=seed,
@@ -464,30 +456,84 @@ class DirectEmulator:
         return err
 
 
-class AutoEncoderEmulator:
-    """Autoencoder-based emulator (emulator.py:521-842): predict only.
+# default parameters of the autoencoder-based emulator (emulator.py:521-525)
+latent_dim = 9
+enc_hidden_dims = [352]
+dec_hidden_dims = [32, 352]
+em_hidden_dims = [352, 352, 352, 224]
 
-    The reference evaluates two Keras models back to back (``emulator`` 7->...->latent, then the
-    autoencoder's ``decoder`` latent->...->451, emulator.py:789-790).  Both are Dense chains, so they
-    are concatenated and evaluated by the same fused kernel in one launch.
+
+def _resolve_training_set(par_train, par_val, par_test, signal_train, signal_val, signal_test, stats):
+    """The reference takes its defaults from the dataset it opens at import (emulator.py:198-204); here the arrays, or
+    ``stats``, or the file named by ``VAE21_DATASET`` (else ``dataset_21cmVAE.h5`` next to this file) supply them."""
+    if par_train is None and signal_train is None and stats is None:
+        ds_path = os.environ.get(DATASET_ENV) or (PATH + "dataset_21cmVAE.h5")
+        if not os.path.isfile(ds_path):
+            raise IOError(
+                "no training set: pass par_train/signal_train (or stats=NormStats), or point "
+                f"{DATASET_ENV} at dataset_21cmVAE.h5 (nothing is downloaded at import, unlike the reference)")
+        d = _load_dataset(ds_path)
+        par_train, par_val, par_test = d["par_train"], d["par_val"], d["par_test"]
+        signal_train, signal_val, signal_test = d["signal_train"], d["signal_val"], d["signal_test"]
+    if stats is None:
+        if par_train is None or signal_train is None:
+            raise ValueError("both par_train and signal_train are needed to compute the normalisation constants")
+        stats = pp.NormStats.from_training_set(par_train, signal_train)
+    return par_train, par_val, par_test, signal_train, signal_val, signal_test, stats
+
+
+class AutoEncoder:
+    """Encoder + decoder pair of the autoencoder-based emulator (emulator.py:445-518): two Dense stacks held as
+    ``DenseModel`` objects.  Only what ``AutoEncoderEmulator.predict`` needs runs on the GPU (the decoder, chained behind the
+    emulator); calling the autoencoder on signals is not part of the hot path and is not implemented."""
+
+    def __init__(self, signal_train=None, enc_hidden_dims=[], dec_hidden_dims=[], latent_dim=9, activation_func="relu", *,  # noqa: B006
+                 n_out=None, device=0):
+        if n_out is None:
+            if signal_train is None:
+                raise ValueError("signal_train (or n_out) is needed for the signal width")
+            n_out = int(np.shape(signal_train)[-1])
+        self.encoder = _gen_model(n_out, enc_hidden_dims, latent_dim, activation_func, name="encoder", device=device)
+        # the reference builds the decoder with in_dim=None (input width inferred on first call, emulator.py:495-501)
+        self.decoder = _gen_model(latent_dim, dec_hidden_dims, n_out, activation_func, name="decoder", device=device)
+
+    def call(self, signals):
+        raise NotImplementedError(
+            "reconstructing signals with the autoencoder (451-wide inputs) is outside the evaluated hot path "
+            "(SURVEY.md section 2: AutoEncoder is out of scope); only AutoEncoderEmulator.predict runs on the GPU")
+
+    __call__ = call
+
+
+class AutoEncoderEmulator:
+    """Autoencoder-based emulator (emulator.py:528-842).  Same constructor and method signatures as the reference.
+
+    ``predict`` evaluates two Keras models back to back in the reference (``emulator`` 7->...->latent, then the autoencoder's
+    ``decoder`` latent->...->451, emulator.py:789-790).  Both are Dense chains, so they are concatenated and evaluated by the
+    same fused kernel in one launch.  ``train`` and ``test_error(use_autoencoder=True)`` (which run the 451-input encoder) are
+    outside the hot path and raise NotImplementedError.
     """
 
+    AE_PATH = PATH + "models/autoencoder_based_emulator/"
+
     def __init__(self, par_train=None, par_val=None, par_test=None, signal_train=None, signal_val=None,
-                 signal_test=None, redshifts=redshifts, frequencies=None, *, stats: Optional[pp.NormStats] = None,
-                 device: int = 0, precision=None):
-        self.par_train, self.par_val, self.par_test = par_train, par_val, par_test
-        self.signal_train, self.signal_val, self.signal_test = signal_train, signal_val, signal_test
+                 signal_test=None, latent_dim=latent_dim, enc_hidden_dims=enc_hidden_dims, dec_hidden_dims=dec_hidden_dims,
+                 em_hidden_dims=em_hidden_dims, activation_func="relu", redshifts=redshifts, frequencies=None, *,
+                 stats: Optional[pp.NormStats] = None, device: int = 0, precision=None):
+        (self.par_train, self.par_val, self.par_test, self.signal_train, self.signal_val, self.signal_test,
+         stats) = _resolve_training_set(par_train, par_val, par_test, signal_train, signal_val, signal_test, stats)
         self.par_labels = ["fstar", "Vc", "fx", "tau", "alpha", "nu_min", "Rmfp"]
-        if stats is None:
-            if par_train is None or signal_train is None:
-                raise IOError("no training set: pass par_train/signal_train or stats=NormStats")
-            stats = pp.NormStats.from_training_set(par_train, signal_train)
         self.stats = stats
         self.device = int(device)
         self.precision = precision
-        self.emulator: Optional[DenseModel] = None
-        self.decoder: Optional[DenseModel] = None
+        n_in = int(np.shape(stats.par_min)[-1])
+        n_out = int(np.shape(stats.sig_mean)[-1])
+        # untrained models of the requested shapes, as the reference builds them (emulator.py:640-665)
+        self.autoencoder = AutoEncoder(None, enc_hidden_dims, dec_hidden_dims, latent_dim, activation_func, n_out=n_out,
+                                       device=self.device)
+        self.emulator = _gen_model(n_in, em_hidden_dims, latent_dim, activation_func, name="ae_emualtor", device=self.device)
         self._chain: Optional[DirectEmulator] = None
+        self._chain_for = None
         if frequencies is None:
             if redshifts is not None:
                 frequencies = redshift2freq(redshifts)
@@ -496,29 +542,50 @@ class AutoEncoderEmulator:
         self.redshifts = redshifts
         self.frequencies = frequencies
 
-    def load_model(self, emulator_path=None, decoder_path=None):
-        base = PATH + "models/autoencoder_based_emulator/"
-        em = keras_h5.load_dense_chain(emulator_path or (base + "ae_emulator.h5"))
-        de = keras_h5.load_dense_chain(decoder_path or (base + "decoder.h5"))
+    @property
+    def decoder(self) -> DenseModel:
+        return self.autoencoder.decoder
+
+    def load_model(self, emulator_path=None, encoder_path=None, decoder_path=None):
+        """Load saved models (emulator.py:667-699); defaults are the files shipped with the reference.
+        Raises IOError if a path does not point to a valid model."""
+        em = keras_h5.load_dense_chain(emulator_path or (self.AE_PATH + "ae_emulator.h5"))
+        en = keras_h5.load_dense_chain(encoder_path or (self.AE_PATH + "encoder.h5"))
+        de = keras_h5.load_dense_chain(decoder_path or (self.AE_PATH + "decoder.h5"))
+        if em.dims[-1] != de.dims[0] or en.dims[-1] != de.dims[0] or en.dims[0] != de.dims[-1]:
+            raise IOError(f"models do not chain: emulator {em.dims}, encoder {en.dims}, decoder {de.dims}")
         self.emulator = DenseModel(em, device=self.device)
-        self.decoder = DenseModel(de, device=self.device)
-        chain = DirectEmulator(stats=self.stats, hidden_dims=[1], device=self.device, precision=self.precision,
-                               redshifts=self.redshifts, frequencies=self.frequencies)
-        chain.emulator = DenseModel(em.concat(de, name="ae_emulator+decoder"), device=self.device)
-        chain.par_test, chain.signal_test = self.par_test, self.signal_test
-        self._chain = chain
+        self.autoencoder.encoder = DenseModel(en, device=self.device)
+        self.autoencoder.decoder = DenseModel(de, device=self.device)
+        self._chain = None
+
+    def _fused_chain(self) -> DirectEmulator:
+        key = (self.emulator, self.autoencoder.decoder)
+        if self._chain is None or self._chain_for != key:
+            chain = DirectEmulator(stats=self.stats, hidden_dims=[1], device=self.device, precision=self.precision,
+                                   redshifts=self.redshifts, frequencies=self.frequencies)
+            chain.emulator = DenseModel(self.emulator.weights.concat(self.autoencoder.decoder.weights, name="ae_emulator+decoder"),
+                                        device=self.device)
+            self._chain, self._chain_for = chain, key
+        self._chain.par_test, self._chain.signal_test = self.par_test, self.signal_test
+        self._chain.frequencies = self.frequencies
+        return self._chain
+
+    def train(self, epochs, ae_callbacks=[], em_callbacks=[], verbose="tqdm"):  # noqa: B006 - reference signature
+        raise NotImplementedError(
+            "training the autoencoder-based emulator (emulator.py:701-768) is outside the evaluated hot path; "
+            "DirectEmulator.train is the supported retraining entry point")
 
     def predict(self, params, precision=None, out=None):
-        if self._chain is None:
-            raise RuntimeError("call load_model() first")
-        return self._chain.predict(params, precision=precision if precision is not None else self.precision, out=out)
+        """emulator.py:770-795: global signal(s) [mK] from astrophysical parameters; ``(451,)`` for exactly one row."""
+        return self._fused_chain().predict(params, precision=precision if precision is not None else self.precision, out=out)
 
-    def test_error(self, relative=True, flow=None, fhigh=None, precision=None):
-        """emulator.py:797-827, fused on the GPU like DirectEmulator.test_error."""
+    def test_error(self, use_autoencoder=False, relative=True, flow=None, fhigh=None, precision=None):
+        """emulator.py:797-842.  The emulator's error is fused on the GPU like DirectEmulator.test_error; the autoencoder's own
+        error (``use_autoencoder=True``) needs the 451-input encoder and is not implemented."""
+        if use_autoencoder:
+            raise NotImplementedError("test_error(use_autoencoder=True) runs the 451-input encoder, which is outside the hot path")
         if self.par_test is None or self.signal_test is None:
             raise ValueError("no test set was given")
-        if self._chain is None:
-            raise ValueError("call load_model() first")
-        self._chain.frequencies = self.frequencies
-        return self._chain.error_of(self.par_test, self.signal_test, relative=relative, flow=flow, fhigh=fhigh,
-                                    precision=precision if precision is not None else self.precision)
+        return self._fused_chain().error_of(self.par_test, self.signal_test, relative=relative, flow=flow, fhigh=fhigh,
+                                            precision=precision if precision is not None else self.precision)

@@ -151,6 +151,16 @@ void vae21_host_trim(void); /* release cached pinned blocks */
 int vae21_get_info(vae21_handle* h, int64_t* kernel_launches, float* last_kernel_ms, int* tc_supported);
 
 /*
+ * Operand-range statistics of the tensor-core paths.  The fp16-based operand formats have a finite range: VAE21_TC_FP16X3 splits
+ * hidden activations into fp16 hi/lo (|h| must stay below 65504), VAE21_TC_FP16E4M3 carries its first-order corrections in e4m3
+ * (saturating at 448: beyond it the corrections lose accuracy and the result degrades towards a one-pass fp16 product).  Every
+ * launch adds the number of epilogue threads that converted a hidden activation beyond the range to a per-handle counter;
+ * *saturated receives it (0 = every launch since the last reset stayed inside the range the error budget was pinned for).
+ * Synchronises the device.  VAE21_TC_BF16X3 and the FP32 path have no such limit.
+ */
+int vae21_get_tc_stats(vae21_handle* h, int64_t* saturated, int reset);
+
+/*
  * Benchmark helper: run the predict kernel `iters` times back to back on
  * device-resident buffers and return the mean device time per launch in ms,
  * measured with CUDA events on the launching stream.

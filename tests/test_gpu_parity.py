@@ -295,13 +295,19 @@ def test_autoencoder_emulator_end_to_end_from_h5(tmp_path, rm, ae_golden):
     g = ae_golden
     em = kh.DenseChainWeights(g["kernels"][:5], g["biases"][:5], g["relu"][:5], name="AE_Emulator")
     de = kh.DenseChainWeights(g["kernels"][5:], g["biases"][5:], g["relu"][5:], name="Decoder")
+    rng = np.random.default_rng(5)
+    en = kh.DenseChainWeights([rng.normal(0, 0.05, (451, 352)).astype(np.float32), rng.normal(0, 0.05, (352, 9)).astype(np.float32)],
+                              [np.zeros(352, np.float32), np.zeros(9, np.float32)], [True, False], name="Encoder")
     kh.save_dense_chain(str(tmp_path / "ae_emulator.h5"), em)
+    kh.save_dense_chain(str(tmp_path / "encoder.h5"), en)
     kh.save_dense_chain(str(tmp_path / "decoder.h5"), de)
     pmin, pmax = rm.prior_par_stats()
     mu = np.linspace(-120, 10, 451).astype(np.float32)
     sd = np.float32(47.5)
     ae = emu.AutoEncoderEmulator(stats=pp.NormStats(pmin, pmax, mu, sd))
-    ae.load_model(str(tmp_path / "ae_emulator.h5"), str(tmp_path / "decoder.h5"))
+    # the reference's positional order: emulator, encoder, decoder (emulator.py:667-672)
+    ae.load_model(str(tmp_path / "ae_emulator.h5"), str(tmp_path / "encoder.h5"), str(tmp_path / "decoder.h5"))
+    assert ae.autoencoder.encoder.weights.dims == [451, 352, 9] and ae.autoencoder.decoder.weights.dims == [9, 32, 352, 451]
     p = rm.draw_params(333, seed=21)
     want = rm.predict(p, g["kernels"], g["biases"], g["relu"], pmin, pmax, mu, sd)
     got = ae.predict(p)

@@ -33,9 +33,9 @@ lib = L.load()
 assert lib.vae21_debug_tc_timing(buf) == 0
 a = np.array(buf[:], dtype=np.int64).reshape(160, 16)
 a = a[a[:, 0] > 0]
-names = ["total"] + [f"operand-ready L{i}" for i in range(5)] + [f"q_empty L{i}" for i in range(5)] + ["ring", "rendezvous", "issue", "chunk setup (incl. its waits)", "own iterations (incl. waits)"]
+names = ["total", "a0 wait", "accumulator-free wait", "ring wait", "operand wait", "issue blocks", "loop iterations (incl. waits)"]
 m = a.mean(axis=0)
-print(f"CTAs reporting: {len(a)}; mean cycles of the first MMA warp per launch")
+print(f"CTAs reporting: {len(a)}; mean cycles of the MMA warp per launch")
 ntile = rows / 128 / 148
 for i, n in enumerate(names):
-    print(f"  {n:18s} {m[i]:12.0f}  {100 * m[i] / m[0]:5.1f}%   {m[i] / ntile:8.0f} cycles/tile")
+    print(f"  {n:32s} {m[i]:12.0f}  {100 * m[i] / m[0]:5.1f}%   {m[i] / ntile:8.0f} cycles/tile")
