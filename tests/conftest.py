@@ -46,6 +46,19 @@ def direct_fixture(rm):
     return {"kernels": ks, "biases": bs, "relu": relu, "mu": mu, "sd": sd, "pmin": pmin, "pmax": pmax}
 
 
+@pytest.fixture(scope="session")
+def trained_fixture():
+    """DirectEmulator architecture with TRAINED-SCALE weights (|W| up to 2.0): the student of the reference's shipped autoencoder-based
+    emulator, trained by this repository's CUDA trainer (tools/make_trained_fixture.py), plus the normalisation constants of its
+    training set and 256 held-out (parameters, teacher signal) pairs."""
+    kh = pkg("keras_h5")
+    w = kh.load_dense_chain(os.path.join(GOLDEN, "direct_trained.h5"))
+    d = np.load(os.path.join(GOLDEN, "direct_trained.npz"))
+    return {"kernels": w.kernels, "biases": w.biases, "relu": [bool(r) for r in w.relu], "mu": d["sig_mean"], "sd": np.float32(d["sig_std"]),
+            "pmin": d["par_min"], "pmax": d["par_max"], "par_test": d["par_test"], "signal_test": d["signal_test"],
+            "path": os.path.join(GOLDEN, "direct_trained.h5")}
+
+
 def have_gpu():
     try:
         return pkg("_lib").device_count() > 0

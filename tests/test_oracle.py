@@ -72,3 +72,43 @@ def test_draw_params_has_exact_zero_fx(rm):
     p = rm.draw_params(5000, seed=9)
     assert (p[:, 2] == 0).sum() > 10
     assert np.all(p[:, 0] > 0) and np.all(p[:, 1] > 0)
+
+
+def _torch_chain64(x, kernels, biases, relu):
+    """An implementation of the Dense chain that shares NO code with oracle/refmath.py: torch.nn.functional.linear in float64
+    (weight = kernel^T, Keras `x @ kernel + bias` semantics of emulator.py:41-47)."""
+    import torch
+    import torch.nn.functional as F
+
+    h = torch.from_numpy(np.asarray(x, np.float64))
+    for k, b, r in zip(kernels, biases, relu):
+        h = F.linear(h, torch.from_numpy(np.asarray(k, np.float64)).T.contiguous(), torch.from_numpy(np.asarray(b, np.float64)))
+        if r:
+            h = torch.clamp_min(h, 0.0)
+    return h.numpy()
+
+
+def test_dense_chain_against_an_independent_implementation(rm, ae_golden, trained_fixture):
+    """`ae_chain.npz:y64` is written by rm.dense_chain itself (make_golden.py), so comparing the oracle with it proves nothing about
+    the oracle.  Pin both -- the oracle and the stored vectors -- to an independent float64 implementation, on the reference's real
+    trained weights and on the trained DirectEmulator-shaped fixture."""
+    g = ae_golden
+    y_t = _torch_chain64(g["x"], g["kernels"], g["biases"], g["relu"])
+    np.testing.assert_allclose(y_t, g["y64"], rtol=0, atol=2e-12)
+    np.testing.assert_allclose(rm.dense_chain(g["x"], g["kernels"], g["biases"], g["relu"], dtype=np.float64), y_t, rtol=0, atol=2e-12)
+    f = trained_fixture
+    x = np.random.default_rng(3).uniform(-1, 1, size=(500, 7)).astype(np.float32)
+    np.testing.assert_allclose(rm.dense_chain(x, f["kernels"], f["biases"], f["relu"], dtype=np.float64),
+                               _torch_chain64(x, f["kernels"], f["biases"], f["relu"]), rtol=0, atol=2e-12)
+
+
+def test_trained_fixture_is_trained_scale_and_emulates_its_teacher(rm, ae_golden, trained_fixture):
+    """The fixture stands in for the reference's absent models/emulator.h5: same architecture and layer names, weights of trained
+    magnitude, and it reproduces the teacher (the reference's shipped AE-based emulator) to about 1 % of the signal amplitude --
+    the accuracy class of tests/test_emulator.py:55-80 (the reference's own DirectEmulator: 0.34 % mean, its retrained one 0.53 %)."""
+    f = trained_fixture
+    assert [k.shape for k in f["kernels"]] == [(7, 288), (288, 352), (352, 288), (288, 224), (224, 451)]
+    assert max(float(np.abs(k).max()) for k in f["kernels"]) > 1.0   # Glorot init stays below 0.15
+    pred = rm.predict(f["par_test"], f["kernels"], f["biases"], f["relu"], f["pmin"], f["pmax"], f["mu"], f["sd"])
+    err = np.sqrt(np.mean((pred - f["signal_test"]) ** 2, axis=1)) / np.max(np.abs(f["signal_test"]), axis=1) * 100
+    assert err.mean() < 1.5 and np.median(err) < 1.2, (err.mean(), np.median(err))
