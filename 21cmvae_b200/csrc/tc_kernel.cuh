@@ -50,7 +50,8 @@ constexpr int MT = 128;
 #endif
 constexpr int EPS = VAE21_TC_EPI_PER_SUB;
 constexpr int NEPI = 128 * EPS;          // epilogue threads
-constexpr int NTHREADS = 128 + NEPI;     // warp 0 producer, warps 1 and 2 MMA issuers, warp 3 idle, warps 4.. epilogue
+constexpr int NTHREADS = 160 + NEPI;     // roles: 0 producer, 1 MMA issuer A, 2-3 prologue, 4..4+NEPI/32-1 epilogue, last = MMA issuer B
+constexpr int WARP_ISSUER_B = 4 + NEPI / 32;  // role index of the second MMA-issuing warp (= its hardware warp)
 constexpr int MAXL = 8;
 constexpr int MAXC = 32;
 constexpr int NFULL = 4;          // ring of "accumulator chunk ready" barriers
@@ -63,7 +64,8 @@ constexpr int DBG = VAE21_TC_ABLATE;
 #define VAE21_TC_TIMING 0  // profiling only: per-CTA cycle counters of the MMA warp's waits (tools/tc_timing.py)
 #endif
 #if VAE21_TC_TIMING
-__device__ long long g_tc_timing[160][16];  // [cta][0 total, 1 a0 wait, 2 accumulator-free wait, 3 ring wait, 4 operand wait, 5 issue blocks, 6 loop iterations]
+__device__ long long g_tc_timing[160][16];
+__device__ unsigned long long g_tc_rec[3][256];  // per issue-table record, summed over CTAs: [0] flagged waits, [1] ring wait, [2] visits  // [cta][0 total, 1 a0 wait, 2 accumulator-free wait, 3 ring wait, 4 operand wait, 5 issue blocks, 6 loop iterations]
 #endif
 constexpr int MAX_SLOTS = 16;
 #ifndef VAE21_TC_CTRL_LAST
@@ -120,10 +122,16 @@ struct Plan {
     int slot_bytes2, nslots2;    // weight ring of the CTA-pair kernel (cta_group::2: each CTA holds half of every B tile)
     int smem_total2;
     int default_cg;              // kernel variant used unless VAE21_TC_CTA_GROUP overrides it
-    int issuers;                 // MMA-issuing warps: 2 (default) or 1 (VAE21_TC_DETERMINISTIC=1: bitwise reproducible sums)
+    int issuers;                 // MMA-issuing warps: 2 (default; they alternate ring slots under a token, so the issue order is fixed) or 1
     int bias_total;
+    int bias_smem;               // floats of the bias image copied to shared memory (the final layer's biases live in s_s0 only)
+    // issue tables (one 16-byte record per ring slot of a tile, see build_iters): word offsets into the bias image, [0] one CTA per
+    // tile, [1] CTA pairs
+    int iter_off[2], n_iter[2];
+    int l0_iters[2];             // ring slots of layer 0 (arrival count of the "a0 may be overwritten" barrier)
+    int off_iter;                // shared-memory copy of the issue table
     // shared-memory carve-up (bytes from the 1024-aligned base)
-    int off_act, off_stage, off_a0, off_ring, off_bias, off_s0, off_obs, off_isig, off_bar, smem_total;
+    int off_act, off_stage, off_a0, off_ring, off_ring2, off_bias, off_s0, off_obs, off_isig, off_bar, smem_total;
     unsigned w_bytes;
     Layer L[MAXL];
     Chunk C[MAXC];
@@ -162,6 +170,97 @@ inline unsigned char f2e4m3(float x) { return static_cast<unsigned char>(__nv_cv
 // and the epilogue multiplies by 1 / S_l.  S_l = 2^11 unless a layer's weights are large (w S_l must stay inside fp16).
 constexpr float A_LO_SCALE = 2048.f;
 
+// ---- issue table -------------------------------------------------------------------------------
+// The MMA-issuing warps do not walk layers and chunks: the host flattens a tile's schedule into one 16-byte record per ring slot
+// ("iteration": 1..4 k-steps of one accumulator chunk), in exactly the order the weight producer fills the ring, and the issuers
+// interpret the records.  Everything an iteration needs is in its record, so the two issuing warps can take alternate records
+// without tracking each other's state (round-2 profile: with per-chunk set-up code and running counters the lone issuing warp was
+// busy executing control instructions for 76 % of the kernel).
+//   w0: A operand cursor (bits 0-15: TMEM column of the hi pairs, or shared-memory offset / 16 from the carve-up base) |
+//       accumulator TMEM column << 16
+//   w1: instruction-descriptor bits of the chunk width ((ncols >> 3) << 17)
+//   w2: ncols (bits 0-8) | k-steps in the slot << 9 (3 bits) | flags << 12 | chunk index in the tile << 20
+//   w3: barrier waits before the issue: byte 0 = accumulator buffer (IT_Q_*), bytes 1-3 = operand-ready barriers (IT_W_*)
+enum : uint32_t {
+    IT_TS = 1u << 12,        // A operand in TMEM
+    IT_FIRST = 1u << 13,     // first k-step of the chunk: the first MMA overwrites the accumulator
+    IT_COMMIT1 = 1u << 14,   // after the MMAs: arrive once / twice on the chunk's "accumulator complete" barrier (bits 14-15 = count; the
+    IT_COMMIT2 = 2u << 14,   //   barrier expects two arrivals: the last two slots of a chunk -- possibly issued by different warps)
+    IT_A0FREE = 1u << 16,    // layer 0: also arrive on "a0 may be overwritten"
+};
+// byte 0 of w3: bits 0-1 = 1 + accumulator ring buffer (0: none); bit 2 = parity of this use within the tile (already inverted: the
+// wait is for the PREVIOUS use's drain); bit 3 = uses per tile odd (parity then alternates with the tile count); bit 4 = first use in
+// the tile (nothing to wait for in the CTA's first tile)
+// bytes 1-3 of w3: bits 0-5 = barrier index in the barrier block (0: none); bit 6 = parity of this use within the tile; bit 7 = uses
+// per tile odd
+constexpr int BAR_IDX_Q_EMPTY = 2 * MAX_SLOTS + NFULL;          // + buffer
+constexpr int BAR_IDX_ACT_READY = 2 * MAX_SLOTS + NFULL + 2;    // + chunk index in the producing layer
+constexpr int BAR_IDX_A0_READY = 2 * MAX_SLOTS + NFULL + 2 + MAX_LCHUNK;
+constexpr int BAR_IDX_A0_FREE = BAR_IDX_A0_READY + 1;
+static_assert(BAR_IDX_A0_FREE < 64, "barrier indices must fit the 6-bit fields of the issue table");
+
+inline bool build_iters(const Plan& P, bool pair, std::vector<uint32_t>& tab, int& l0_iters, std::string& why) {
+    tab.clear();
+    l0_iters = 0;
+    int U_q[2] = {0, 0}, U_act[MAX_LCHUNK] = {0, 0, 0, 0};  // uses per tile
+    for (int c = 0; c < P.n_chunks; ++c)
+        if (P.C[c].qbuf >= 0) ++U_q[P.C[c].qbuf];
+    for (int l = 1; l < P.n_layers; ++l)
+        for (int j = 0; j < P.L[l - 1].nchunks; ++j) ++U_act[j];
+    int u_q[2] = {0, 0}, u_act[MAX_LCHUNK] = {0, 0, 0, 0};
+    for (int c = 0; c < P.n_chunks; ++c) {
+        const Chunk& C = P.C[c];
+        const int kps = pair ? C.kps2 : 1, nst = C.nstages;
+        const int niter = (nst + kps - 1) / kps;
+        const bool ts = (C.a_src == A_TMEM);
+        int src = -1, src_end = -1, next_src_k = 0x7fffffff;  // chunks of the producing layer still to wait for
+        if (C.layer > 0 && C.idx_in_layer == 0) {
+            src = C.src_first;
+            src_end = src + C.src_count;
+            next_src_k = 0;
+        }
+        for (int s = 0, i = 0; s < nst; s += kps, ++i) {
+            const int nk = std::min(kps, nst - s);
+            const uint32_t a = ts ? static_cast<uint32_t>(16 * s)
+                                  : static_cast<uint32_t>(((C.a_src == A_SMEM_A0 ? P.off_a0 : P.off_act) + s * KSTEP_BYTES) >> 4);
+            if (a > 0xffffu) { why = "internal: A cursor does not fit the issue table"; return false; }
+            uint32_t w2 = static_cast<uint32_t>(C.ncols) | (static_cast<uint32_t>(nk) << 9) | (static_cast<uint32_t>(c) << 20);
+            if (ts) w2 |= IT_TS;
+            if (s == 0) w2 |= IT_FIRST;
+            if (i == niter - 1) w2 |= (niter == 1) ? IT_COMMIT2 : IT_COMMIT1;
+            else if (i == niter - 2) w2 |= IT_COMMIT1;
+            if (C.layer == 0) {
+                w2 |= IT_A0FREE;
+                ++l0_iters;
+            }
+            uint32_t w3 = 0;
+            if (s == 0 && C.qbuf >= 0) {
+                const int u = u_q[C.qbuf]++;
+                w3 |= static_cast<uint32_t>(1 + C.qbuf) | (static_cast<uint32_t>((u ^ 1) & 1) << 2) |
+                      (static_cast<uint32_t>(U_q[C.qbuf] & 1) << 3) | (static_cast<uint32_t>(u == 0) << 4);
+            }
+            int nw = 0;
+            auto add_wait = [&](int bar_idx, int u, int U) {
+                ++nw;
+                if (nw <= 3) w3 |= (static_cast<uint32_t>(bar_idx) | (static_cast<uint32_t>(u & 1) << 6) | (static_cast<uint32_t>(U & 1) << 7)) << (8 * nw);
+            };
+            if (s == 0 && C.layer == 0 && C.idx_in_layer == 0) add_wait(BAR_IDX_A0_READY, 0, 1);
+            while (s + nk - 1 >= next_src_k) {  // the k-steps of this slot reach into the next chunk of the producing layer
+                const int j = src - C.src_first;
+                add_wait(BAR_IDX_ACT_READY + j, u_act[j]++, U_act[j]);
+                ++src;
+                next_src_k = (src < src_end) ? (P.C[src].n0 >> 4) : 0x7fffffff;
+            }
+            if (nw > 3) { why = "more than three operand waits in one ring slot"; return false; }
+            tab.push_back(a | (static_cast<uint32_t>(C.dcol) << 16));
+            tab.push_back(static_cast<uint32_t>(C.ncols >> 3) << 17);
+            tab.push_back(w2);
+            tab.push_back(w3);
+        }
+    }
+    return true;
+}
+
 // Build the schedule for a Dense stack.  Returns false (with `why`) when the stack does not fit.
 inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, const float* const* kernels,
                             const float* const* biases, const int* relu, Plan& P,
@@ -173,7 +272,6 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
     if (dims[0] > 16) { why = "more than 16 input parameters"; return false; }
     P.n_layers = n_layers;
     P.default_cg = 2;
-    P.issuers = std::getenv("VAE21_TC_DETERMINISTIC") ? 1 : 2;
     P.K0 = dims[0];
     P.n_out = dims[n_layers];
     auto pad16 = [](int x) { return (x + 15) / 16 * 16; };
@@ -284,6 +382,36 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
     P.slot_bytes = 0;
     for (int c = 0; c < nchunks; ++c) P.slot_bytes = std::max(P.slot_bytes, P.C[c].ncols * 16 * 2 * 2);
 
+    // ring slot geometry (independent of the shared-memory carve-up).  Pair kernel: each CTA holds half of every B tile, so a slot
+    // of the same size holds TWO k-steps: the same bytes in flight with half as many barrier round trips (the ring protocol is
+    // latency-, not bandwidth-bound); narrow chunks would leave most of a slot empty (112 columns: half), so up to 4 k-steps of
+    // this CTA's half tile are packed into a slot.
+    P.slot_bytes2 = P.slot_bytes / 2 * VAE21_TC_KPS;
+    static const int kps_max = std::getenv("VAE21_TC_KPS_MAX") ? std::min(4, std::atoi(std::getenv("VAE21_TC_KPS_MAX"))) : 4;  // the issue loop unrolls 4
+    for (int c = 0; c < nchunks; ++c)
+        P.C[c].kps2 = std::max(VAE21_TC_KPS, std::min(std::max(kps_max, VAE21_TC_KPS), P.slot_bytes2 / (P.C[c].ncols * 32)));
+    for (int c = 0; c < nchunks; ++c) {  // denormalised per-chunk records (the issue tables below read them)
+        Chunk& C = P.C[c];
+        const Layer& L = P.L[C.layer];
+        C.idx_in_layer = c - L.first_chunk;
+        C.last_in_layer = (c == L.first_chunk + L.nchunks - 1) ? 1 : 0;
+        C.a_src = L.a_src;
+        C.out_dst = L.out_dst;
+        C.relu = L.relu;
+        C.bias_n0 = L.bias_off + C.n0;
+        C.src_first = 0;
+        C.src_count = 0;
+        if (C.layer > 0 && C.idx_in_layer == 0) {
+            C.src_first = P.L[C.layer - 1].first_chunk;
+            C.src_count = P.L[C.layer - 1].nchunks;
+        }
+    }
+    P.n_iter[0] = P.n_iter[1] = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        P.n_iter[0] += P.C[c].nstages;
+        P.n_iter[1] += (P.C[c].nstages + P.C[c].kps2 - 1) / P.C[c].kps2;
+    }
+
     // shared memory
     int off = 0;
     P.off_act = off;
@@ -302,7 +430,8 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
     P.off_a0 = off;
     off += KSTEP_BYTES;
     P.off_bias = off;
-    off += P.bias_total * 4;
+    P.bias_smem = P.L[last].bias_off;  // hidden layers only: the final layer's biases are folded into s_s0
+    off += P.bias_smem * 4;
     const int nop = pad16(P.n_out);
     P.off_s0 = off;
     off += nop * 4;
@@ -312,26 +441,19 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
     off += nop * 4;
     P.off_bar = off;
     off += BAR_BYTES + 2 * 16 * 4 + 4 * (EPS - 1) * 128 * 4;  // barriers + prologue constants + chi^2 / amplitude partials
-    off = (off + 127) / 128 * 128;
-    P.off_ring = off;
-    const int avail = SMEM_LIMIT - 128 /*alignment slack*/ - off;
-    P.nslots = std::min(MAX_SLOTS, avail / P.slot_bytes);
+    P.off_iter = off;  // issue table of the kernel variant that runs, then its weight ring
+    const int off1 = (off + P.n_iter[0] * 16 + 127) / 128 * 128, off2 = (off + P.n_iter[1] * 16 + 127) / 128 * 128;
+    P.off_ring = off1;
+    P.off_ring2 = off2;
+    // Even slot counts: with two issuing warps alternating slots, every use of a slot must be observed by the SAME warp (mbarrier
+    // waits are by phase parity: a warp that saw only every other use of a slot would pass on a stale completion).
+    P.nslots = std::min(MAX_SLOTS, (SMEM_LIMIT - 128 /*alignment slack*/ - off1) / P.slot_bytes) & ~1;
     if (P.nslots < 2) { why = "shared memory: activations leave no room for a weight ring"; return false; }
-    // pair kernel: each CTA holds half of every B tile, so a slot of the same size holds TWO k-steps: the same bytes
-    // in flight with half as many barrier round trips (the ring protocol is latency-, not bandwidth-bound)
-    P.slot_bytes2 = P.slot_bytes / 2 * VAE21_TC_KPS;
-    P.nslots2 = std::min(MAX_SLOTS, avail / P.slot_bytes2) & ~1;  // even: the MMA loop consumes slots in pairs
-    // narrow chunks would leave most of a slot empty (112 columns: half): pack up to 4 k-steps of this CTA's half tile into a slot
-    static const int kps_max = std::getenv("VAE21_TC_KPS_MAX") ? std::min(4, std::atoi(std::getenv("VAE21_TC_KPS_MAX"))) : 4;  // the issue loop unrolls 4
-    for (int c = 0; c < nchunks; ++c)
-        P.C[c].kps2 = std::max(VAE21_TC_KPS, std::min(std::max(kps_max, VAE21_TC_KPS), P.slot_bytes2 / (P.C[c].ncols * 32)));
-    P.smem_total2 = off + P.nslots2 * P.slot_bytes2 + 128;
-    // Two issuing warps alternate loop iterations of two slots each.  mbarrier waits are by phase PARITY, so each
-    // issuer must observe every ring cycle at least once: with fewer than 4 slots (one iteration per cycle) an issuer
-    // would skip every other phase of its slots and pass its wait on a stale completion.  Use one issuer then.
-    if (std::min(P.nslots, P.nslots2) < 4) P.issuers = 1;
-    off += P.nslots * P.slot_bytes;
-    P.smem_total = off + 128;
+    P.nslots2 = std::min(MAX_SLOTS, (SMEM_LIMIT - 128 - off2) / P.slot_bytes2) & ~1;
+    P.smem_total2 = off2 + P.nslots2 * P.slot_bytes2 + 128;
+    P.smem_total = off1 + P.nslots * P.slot_bytes + 128;
+    static const int issuers_env = std::getenv("VAE21_TC_ISSUERS") ? std::atoi(std::getenv("VAE21_TC_ISSUERS")) : 2;
+    P.issuers = issuers_env == 1 ? 1 : 2;
 
     // Weight images, in exactly the order the MMA warp consumes them: chunk -> k-step -> {hi, lo} tile,
     // tile = [2 k-groups][rows][8 elements]  (B operand, "K-major": row n holds W[k][n]).
@@ -347,23 +469,7 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
         while (S > 1.f && wmax * S > 32768.f) S *= 0.5f;
         P.L[l].inv_s8 = 1.f / S;
     }
-    for (int c = 0; c < nchunks; ++c) {
-        Chunk& C = P.C[c];
-        const Layer& L = P.L[C.layer];
-        C.idx_in_layer = c - L.first_chunk;
-        C.last_in_layer = (c == L.first_chunk + L.nchunks - 1) ? 1 : 0;
-        C.a_src = L.a_src;
-        C.out_dst = L.out_dst;
-        C.relu = L.relu;
-        C.bias_n0 = L.bias_off + C.n0;
-        C.inv_s8 = L.inv_s8;
-        C.src_first = 0;
-        C.src_count = 0;
-        if (C.layer > 0 && C.idx_in_layer == 0) {
-            C.src_first = P.L[C.layer - 1].first_chunk;
-            C.src_count = P.L[C.layer - 1].nchunks;
-        }
-    }
+    for (int c = 0; c < nchunks; ++c) P.C[c].inv_s8 = P.L[P.C[c].layer].inv_s8;
 
     const size_t img2 = P.w_bytes / 2;  // element offset of image 2
     for (int c = 0; c < nchunks; ++c) {
@@ -412,6 +518,15 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
     bias_img.assign(P.bias_total, 0.f);
     for (int l = 0; l < n_layers; ++l)
         for (int n = 0; n < dims[l + 1]; ++n) bias_img[P.L[l].bias_off + n] = biases[l][n];
+    // issue tables, appended to the bias image (raw 32-bit words)
+    for (int v = 0; v < 2; ++v) {
+        std::vector<uint32_t> tab;
+        if (!build_iters(P, v == 1, tab, P.l0_iters[v], why)) return false;
+        if (static_cast<int>(tab.size()) != 4 * P.n_iter[v]) { why = "internal: issue table size"; return false; }
+        P.iter_off[v] = static_cast<int>(bias_img.size());
+        bias_img.resize(bias_img.size() + tab.size());
+        std::memcpy(bias_img.data() + P.iter_off[v], tab.data(), tab.size() * 4);
+    }
     return true;
 }
 
@@ -771,15 +886,22 @@ __device__ __noinline__ void prologue_row(const LaunchArgs& a, const NormConsts&
         grid_point(a, static_cast<unsigned long long>(a.row_base + grow), K0, x);
         return;
     }
+    if (a.in_mode == IN_NORMALISED_F32) {
+#pragma unroll 1
+        for (int j = 0; j < K0; ++j) x[j] = reinterpret_cast<const float*>(a.in)[grow * K0 + j];
+        return;
+    }
+    const bool f32_in = (a.in_mode == IN_PARAMS_F32);
+    // all raw parameters of the row first: independent loads, ONE memory latency per row instead of one per parameter
+    double pv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (j < K0)
+            pv[j] = f32_in ? static_cast<double>(reinterpret_cast<const float*>(a.in)[grow * K0 + j]) : reinterpret_cast<const double*>(a.in)[grow * K0 + j];
+    }
 #pragma unroll 1
     for (int j = 0; j < K0; ++j) {
-        const long long g = grow * K0 + j;
-        if (a.in_mode == IN_NORMALISED_F32) {
-            x[j] = reinterpret_cast<const float*>(a.in)[g];
-            continue;
-        }
-        const bool f32_in = (a.in_mode == IN_PARAMS_F32);
-        double p = f32_in ? static_cast<double>(reinterpret_cast<const float*>(a.in)[g]) : reinterpret_cast<const double*>(a.in)[g];
+        double p = pv[j];
         if (j == nc.floor_col && p == 0.0) p = f32_in ? static_cast<double>(static_cast<float>(nc.floor_val)) : nc.floor_val;
         double t = p;
         if (nc.log_mask[j]) {
@@ -817,7 +939,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     const int tid = threadIdx.x, lane = tid & 31;
     const int hw_warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 #if VAE21_TC_CTRL_LAST
-    const int warp = hw_warp < NEPI / 32 ? hw_warp + 4 : hw_warp - NEPI / 32;
+    const int warp = hw_warp < NEPI / 32 ? hw_warp + 4 : (hw_warp < NEPI / 32 + 4 ? hw_warp - NEPI / 32 : hw_warp);
 #else
     const int warp = hw_warp;
 #endif
@@ -833,10 +955,10 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     auto bar_ring_full = [&](int s) { return bar0 + 8u * s; };
     auto bar_ring_empty = [&](int s) { return bar0 + 8u * (MAX_SLOTS + s); };
     auto bar_chunk_full = [&](int i) { return bar0 + 8u * (2 * MAX_SLOTS + i); };
-    auto bar_q_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + NFULL + b); };
-    auto bar_act_ready = [&](int j) { return bar0 + 8u * (2 * MAX_SLOTS + NFULL + 2 + j); };  // j < MAX_LCHUNK
-    const uint32_t bar_a0_ready = bar0 + 8u * (2 * MAX_SLOTS + NFULL + 2 + MAX_LCHUNK);
-    const uint32_t bar_a0_free = bar0 + 8u * (2 * MAX_SLOTS + NFULL + 3 + MAX_LCHUNK);  // layer-0 MMAs of the tile have read a0
+    auto bar_q_empty = [&](int b) { return bar0 + 8u * (BAR_IDX_Q_EMPTY + b); };
+    auto bar_act_ready = [&](int j) { return bar0 + 8u * (BAR_IDX_ACT_READY + j); };  // j < MAX_LCHUNK
+    const uint32_t bar_a0_ready = bar0 + 8u * BAR_IDX_A0_READY;
+    const uint32_t bar_a0_free = bar0 + 8u * BAR_IDX_A0_FREE;  // layer-0 MMAs of the tile have read a0
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + P.off_bar + 8 * (2 * MAX_SLOTS + NFULL + 4 + MAX_LCHUNK));
     float* s_chi = reinterpret_cast<float*>(sm + P.off_bar + BAR_BYTES) + 32;  // [2][EPS-1][128] chi^2 partials of the other column shares
     float* s_amp = s_chi + 2 * (EPS - 1) * 128;                                 // [2][EPS-1][128] |truth| maxima (OM_ERROR)
@@ -856,17 +978,22 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         // epilogue -> MMA hand-offs: ONE arrival per epilogue warp (elected lane after __syncwarp).  In a pair the follower's epilogue
         // warps arrive DIRECTLY on the leader's barriers (remote arrive), so those count both CTAs.
         const uint32_t both = (PAIR && leader) ? 2u : 1u;
-        for (int i = 0; i < NFULL; ++i) mbar_init(bar_chunk_full(i), 1);
+        for (int i = 0; i < NFULL; ++i) mbar_init(bar_chunk_full(i), 2);  // the commits behind the last two ring slots of a chunk
         for (int b = 0; b < 2; ++b) mbar_init(bar_q_empty(b), (NEPI / 32) * both);
         for (int j = 0; j < MAX_LCHUNK; ++j) mbar_init(bar_act_ready(j), (NEPI / 32) * both);
         mbar_init(bar_a0_ready, 2 * both);  // one arrival from each of the two prologue warps (of each CTA)
-        mbar_init(bar_a0_free, 1);
+        mbar_init(bar_a0_free, static_cast<uint32_t>(P.l0_iters[PAIR ? 1 : 0]));  // one commit behind every ring slot of layer 0
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     {
         const Layer& LL = P.L[P.n_layers - 1];
         const int nop = LL.Npad;
-        for (int i = tid; i < P.bias_total; i += NTHREADS) s_bias[i] = bias_g[i];
+        for (int i = tid; i < P.bias_smem; i += NTHREADS) s_bias[i] = bias_g[i];
+        {  // this kernel variant's issue table (raw words behind the biases)
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(bias_g) + P.iter_off[PAIR ? 1 : 0];
+            uint32_t* dst = reinterpret_cast<uint32_t*>(sm + P.off_iter);
+            for (int i = tid; i < 4 * P.n_iter[PAIR ? 1 : 0]; i += NTHREADS) dst[i] = src[i];
+        }
         for (int n = tid; n < nop; n += NTHREADS) {
             const float b = bias_g[LL.bias_off + n];
             float s0 = b, ob = 0.f, is = 0.f;
@@ -898,7 +1025,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     tc_fence_after();
     const uint32_t tm = *tmem_slot;
     const int n_chunks = P.n_chunks, nslots = PAIR ? P.nslots2 : P.nslots;
-    const uint32_t ring0 = base + P.off_ring, slot_bytes = static_cast<uint32_t>(PAIR ? P.slot_bytes2 : P.slot_bytes);
+    const uint32_t ring0 = base + (PAIR ? P.off_ring2 : P.off_ring), slot_bytes = static_cast<uint32_t>(PAIR ? P.slot_bytes2 : P.slot_bytes);
 
     if (warp == 0) {
         // ===================== producer: stream the weight image through the ring ============
@@ -934,181 +1061,210 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             }
         }
     } else if (warp == 1 && PAIR && !leader) {
-        // ===================== follower of a pair: relay "my half of this ring slot has landed" to the issuer =========
+        // ===================== follower of a pair: relay "my half of this ring slot has landed" to the issuers =========
         // (a bulk copy cannot signal a barrier in another CTA; the leader's MMAs read both CTAs' halves)
         int slot = 0;
         uint32_t rphase = 0;
+        const int n_iter = P.n_iter[1];
 #pragma unroll 1
         for (long long unit = unit0; unit < nunits; unit += ustep) {
 #pragma unroll 1
-            for (int c = 0; c < n_chunks; ++c) {
-                const int nst = P.C[c].nstages, kps = P.C[c].kps2;
-#pragma unroll 1
-                for (int s = 0; s < nst; s += kps) {
-                    mbar_wait(bar_ring_full(slot), rphase);
-                    if (lane == 0) mbar_arrive_remote(bar_ring_full(slot), 0);
-                    __syncwarp();
-                    if (++slot == nslots) {
-                        slot = 0;
-                        rphase ^= 1u;
-                    }
+            for (int it = 0; it < n_iter; ++it) {
+                mbar_wait(bar_ring_full(slot), rphase);
+                if (lane == 0) mbar_arrive_remote(bar_ring_full(slot), 0);
+                __syncwarp();
+                if (++slot == nslots) {
+                    slot = 0;
+                    rphase ^= 1u;
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer ====================================================
-        // ONE warp issues every tcgen05.mma of the CTA (pair), in program order: the accumulation order -- hence every output bit --
-        // is fixed (tcgen05 instructions of different threads are unordered).  The whole warp runs the (warp-uniform) loop, only the
-        // tcgen05 instructions are predicated on one elected lane.  One ring slot (1..4 k-steps) per iteration.
-        int slot = 0;
-        uint32_t rphase = 0;
-        uint32_t seq = 0;                 // running chunk counter (chunk_full ring)
-        uint32_t q_use0 = 0, q_use1 = 0;  // uses so far of each ring accumulator
-        uint32_t act_cnt[MAX_LCHUNK] = {0, 0, 0, 0};
-        uint32_t a0_cnt = 0;
-        const uint32_t fmtbits = (FMT == 0) ? 1u : 0u;
-        const uint32_t idesc_base = (1u << 4) | (fmtbits << 7) | (fmtbits << 10) | ((static_cast<uint32_t>(CG * 128) >> 4) << 24);
-        // descriptor high words are constant: SBO = 128 B, version 1; LBO goes into the low word
-        const uint32_t desc_hi = (128u >> 4) | (1u << 14);
-        const uint32_t a_lbo = (static_cast<uint32_t>(A_KG_BYTES) >> 4) << 16;
-        const uint32_t slot16 = slot_bytes >> 4;
+    } else if ((warp == 1 || warp == WARP_ISSUER_B) && (!PAIR || leader)) {
+        // ===================== MMA issuers ===================================================
+        // The issuers interpret the tile's issue table (build_iters): one record per ring slot.  With two issuers (the default), warp
+        // `me` takes the records with global index g = me (mod 2) and a token -- two named barriers used as a baton, with
+        // tcgen05.fence on both sides -- orders the MMAs of record g behind those of record g - 1: every tcgen05.mma of the CTA
+        // (pair) is issued in table order, so the accumulation order, hence every output bit, is fixed, while each warp's barrier
+        // waits, record decoding and descriptor set-up overlap the other warp's issue.  The whole warp runs the (warp-uniform) loop;
+        // only the tcgen05 instructions are predicated on one elected lane.
+        const int me = (warp == 1) ? 0 : 1;
+        const int nis = P.issuers;
+        const int n_iter = P.n_iter[PAIR ? 1 : 0];
+        if (me < nis && unit0 < nunits) {
+            const uint4* tab = reinterpret_cast<const uint4*>(sm + P.off_iter);
+            const uint32_t fmtbits = (FMT == 0) ? 1u : 0u;
+            const uint32_t idesc_base = (1u << 4) | (fmtbits << 7) | (fmtbits << 10) | ((static_cast<uint32_t>(CG * 128) >> 4) << 24);
+            // descriptor high words are constant: SBO = 128 B, version 1; LBO goes into the low word
+            const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+            const uint32_t a_base32 = ((base & 0x3FFFFu) >> 4) | ((static_cast<uint32_t>(A_KG_BYTES) >> 4) << 16);
+            const uint32_t ring16 = (ring0 & 0x3FFFFu) >> 4, slot16 = slot_bytes >> 4;
 #if VAE21_TC_TIMING
-        long long tm_total = clock64(), tm_a0 = 0, tm_q = 0, tm_ring = 0, tm_opnd = 0, tm_issue = 0, tm_iter = 0;
+            long long tm_total = clock64(), tm_flag = 0, tm_ring = 0, tm_token = 0, tm_issue = 0;
 #define TSTART const long long t_s_ = clock64();
 #define TADD(var) var += clock64() - t_s_;
 #else
 #define TSTART
 #define TADD(var)
 #endif
-        auto wait_ev = [&](uint32_t bar, uint32_t parity) {
-            if (PAIR) mbar_wait_cluster(bar, parity);
-            else mbar_wait(bar, parity);
-        };
+            long long unit = unit0;
+            const uint32_t last_owner = static_cast<uint32_t>((((nunits - unit0 + ustep - 1) / ustep) * n_iter - 1) & 1);
+            uint32_t tpar = 0;      // parity of the CTA's tile count
+            uint32_t first_tile = 1;
+            uint32_t seq_base = 0;  // chunks of earlier tiles (index of the chunk_full ring)
+            int it = me, slot = me;  // n_iter >= 2, nslots >= 2
+            uint32_t rphase = 0;
+            bool started = false;   // this warp has passed at least one token wait / the other has issued before
+            uint4 rec = tab[it];
 #pragma unroll 1
-        for (long long unit = unit0; unit < nunits; unit += ustep) {
-#pragma unroll 1
-            for (int c = 0; c < n_chunks; ++c) {
-                const Chunk& C = P.C[c];
-                // Operand readiness is tracked per chunk of the PRODUCING layer: k-step s of this layer only needs
-                // the 16 features [16 s, 16 s + 16), so the first chunk of a layer starts as soon as the first chunk of
-                // the previous layer has been converted and waits for the later ones when it reaches their k range.
-                int src = -1, src_end = -1;  // chunks of the producing layer still to wait for
-                if (C.idx_in_layer == 0) {
-                    if (C.layer == 0) {
-                        { TSTART wait_ev(bar_a0_ready, a0_cnt & 1u); TADD(tm_a0) }
-                        ++a0_cnt;
-                    } else {
-                        src = C.src_first;
-                        src_end = src + C.src_count;
-                    }
-                }
-                if (C.qbuf >= 0) {  // accumulator buffer must have been drained by the epilogue
-                    const uint32_t u = C.qbuf ? q_use1 : q_use0;
-                    if (C.qbuf) ++q_use1; else ++q_use0;
-                    if (u > 0) { TSTART wait_ev(bar_q_empty(C.qbuf), (u - 1u) & 1u); TADD(tm_q) }
-                }
-                const uint32_t idesc = idesc_base | (static_cast<uint32_t>(C.ncols >> 3) << 17);
-                const uint32_t d = tm + static_cast<uint32_t>(C.dcol);
-                const uint32_t b_kg = static_cast<uint32_t>(C.ncols / CG) * 16u;  // bytes between B k-groups (this CTA's rows)
-                const uint32_t b_lo16 = (b_kg * 2u) >> 4;                         // hi tile -> second tile, in 16 B units
-                const uint32_t kstep16 = b_kg * 4u >> 4;                          // one k-step of this CTA's B rows, in 16 B units
-                // low descriptor words: (address >> 4) | (LBO >> 4) << 16; slots are slot16 apart
-                const uint32_t b_base32 = ((ring0 & 0x3FFFFu) >> 4) | ((b_kg >> 4) << 16);
-                const bool ts = (C.a_src == A_TMEM);
-                // A operand cursor: TMEM column (16 per k-step) or low descriptor word (KSTEP_BYTES per k-step)
-                uint32_t acur = ts ? tm : ((((base + (C.a_src == A_SMEM_A0 ? P.off_a0 : P.off_act)) & 0x3FFFFu) >> 4) | a_lbo);
-                const uint32_t astep = ts ? 16u : static_cast<uint32_t>(KSTEP_BYTES >> 4);
-                const uint32_t a2off = ts ? 8u : ((2u * A_KG_BYTES) >> 4);
-                const int nst = C.nstages, kps = PAIR ? C.kps2 : 1;
-                int next_src_k = (src >= 0) ? 0 : 0x7fffffff;  // k-step at which the next producing chunk starts
-#pragma unroll 1
-                for (int s = 0; s < nst; s += kps) {
+            while (true) {
+                // next record (prefetched: the load overlaps this iteration's waits)
+                int it_n = it + nis;
+                const bool roll = it_n >= n_iter;
+                if (roll) it_n -= n_iter;
+                const uint4 nxt = tab[it_n];
+
+                const uint32_t w2 = rec.z, w3 = rec.w;
+                const uint32_t ncols = w2 & 0x1ffu;
+                const int nk = static_cast<int>((w2 >> 9) & 7u);
+                const uint32_t full = bar_ring_full(slot);
+                {
+                    TSTART
+                    if (!mbar_try(full, rphase)) mbar_wait(full, rphase);
+                    TADD(tm_ring)
 #if VAE21_TC_TIMING
-                    const long long t_it0 = clock64();
+                    if (lane == 0 && it < 256) atomicAdd(&g_tc_rec[1][it], static_cast<unsigned long long>(clock64() - t_s_));
 #endif
-                    const int nk = min(kps, nst - s);
-                    const uint32_t full = bar_ring_full(slot);
-                    { TSTART if (!mbar_try(full, rphase)) mbar_wait(full, rphase); TADD(tm_ring) }
-                    if (s + nk - 1 >= next_src_k) {  // the k-steps of this slot reach into the next chunk of the producing layer
-                        TSTART
-                        do {
-                            const int j = src - C.src_first;
-                            wait_ev(bar_act_ready(j), (act_cnt[j]++) & 1u);
-                            ++src;
-                            next_src_k = (src < src_end) ? (P.C[src].n0 >> 4) : 0x7fffffff;
-                        } while (s + nk - 1 >= next_src_k);
-                        TADD(tm_opnd)
-                    }
-                    tc_fence_after();
-                    {
-                        TSTART
-                        if (elect_one()) {
-                            // up to 4 k-steps per slot, fully unrolled: the loop-invariant operands are moved to uniform registers once
-                            // per slot, not once per k-step (a rolled loop re-did 8 R2UR per k-step: ~125 issue cycles per k-step)
-                            const uint32_t bj = b_base32 + slot * slot16;
+                }
+                if (nis == 2 && (started || me == 1)) {  // the baton: the other warp has issued the previous record
+                    TSTART
+                    if (me == 0) asm volatile("bar.sync 3, 64;\n" ::: "memory");
+                    else asm volatile("bar.sync 2, 64;\n" ::: "memory");
+                    TADD(tm_token)
+                }
+                // Accumulator buffer drained / operands converted (at most a few records per chunk).  These waits come AFTER the baton:
+                // mbarrier waits are by phase parity, and a wait for phase n + 1 only means something once phase n is known to be over
+                // -- which the owner of an earlier record has waited for before issuing it.
+                if (w3) {
+                    TSTART
+                    const uint32_t q = w3 & 0xffu;
+                    if ((q & 3u) && !((q & 16u) && first_tile))
+                        mbar_wait(bar0 + 8u * (BAR_IDX_Q_EMPTY + (q & 3u) - 1u), ((q >> 2) ^ ((q >> 3) & tpar)) & 1u);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                if (j < nk && !(DBG & 1))
-                                    kstep_mma<FMT, PAIR>(ts, d, acur + j * astep, acur + j * astep + a2off, bj + j * kstep16, bj + j * kstep16 + b_lo16,
-                                                         desc_hi, idesc, (j > 0 || s > 0) ? 1u : 0u);
-                            }
-                            // the slot is freed -- in both CTAs of a pair -- by a commit behind the MMAs of its last k-step
-                            if (PAIR) mma2_commit_both(full + 8u * MAX_SLOTS);
-                            else mma_commit(full + 8u * MAX_SLOTS);
+                    for (int i = 1; i < 4; ++i) {
+                        const uint32_t e = (w3 >> (8 * i)) & 0xffu;
+                        if (e) mbar_wait(bar0 + 8u * (e & 63u), ((e >> 6) ^ ((e >> 7) & tpar)) & 1u);
+                    }
+                    TADD(tm_flag)
+#if VAE21_TC_TIMING
+                    if (lane == 0 && it < 256) atomicAdd(&g_tc_rec[0][it], static_cast<unsigned long long>(clock64() - t_s_));
+#endif
+                }
+#if VAE21_TC_TIMING
+                if (lane == 0 && it < 256) atomicAdd(&g_tc_rec[2][it], 1ull);
+#endif
+                started = true;
+                tc_fence_after();
+                {
+                    TSTART
+                    if (elect_one()) {
+                        const uint32_t idesc = idesc_base | rec.y;
+                        const uint32_t d = tm + (rec.x >> 16);
+                        const bool ts = (w2 & IT_TS) != 0;
+                        const uint32_t b_kg16 = ncols / CG;                     // bytes between B k-groups (this CTA's rows) / 16
+                        const uint32_t bj = ring16 + slot * slot16 + (b_kg16 << 16);  // low descriptor word of the slot's first hi tile
+                        const uint32_t b_lo16 = 2u * b_kg16, kstep16 = 4u * b_kg16;    // hi tile -> second tile, k-step -> k-step (16 B units)
+                        const uint32_t acur = ts ? tm + (rec.x & 0xffffu) : a_base32 + (rec.x & 0xffffu);
+                        const uint32_t astep = ts ? 16u : static_cast<uint32_t>(KSTEP_BYTES >> 4);
+                        const uint32_t a2off = ts ? 8u : ((2u * A_KG_BYTES) >> 4);
+                        const uint32_t acc0 = (w2 & IT_FIRST) ? 0u : 1u;
+                        // up to 4 k-steps per slot, fully unrolled
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (j < nk && !(DBG & 1))
+                                kstep_mma<FMT, PAIR>(ts, d, acur + j * astep, acur + j * astep + a2off, bj + j * kstep16, bj + j * kstep16 + b_lo16,
+                                                     desc_hi, idesc, j > 0 ? 1u : acc0);
                         }
-                        __syncwarp();
-                        TADD(tm_issue)
+                        // the slot is freed -- in both CTAs of a pair -- by a commit behind the MMAs of its last k-step
+                        if (PAIR) mma2_commit_both(full + 8u * MAX_SLOTS);
+                        else mma_commit(full + 8u * MAX_SLOTS);
+                        const uint32_t ncommit = (w2 >> 14) & 3u;
+                        if (ncommit) {
+                            const uint32_t cf = bar_chunk_full((seq_base + (w2 >> 20)) & (NFULL - 1));
+                            if (PAIR) mma2_commit_both(cf);
+                            else mma_commit(cf);
+                            if (ncommit == 2) {
+                                if (PAIR) mma2_commit_both(cf);
+                                else mma_commit(cf);
+                            }
+                        }
+                        if (w2 & IT_A0FREE) {  // the prologue warp may overwrite a0 once the layer-0 MMAs are done
+                            if (PAIR) mma2_commit_both(bar_a0_free);
+                            else mma_commit(bar_a0_free);
+                        }
                     }
-                    acur += astep * static_cast<uint32_t>(nk);
-                    if (++slot == nslots) {
-                        slot = 0;
-                        rphase ^= 1u;
-                    }
-#if VAE21_TC_TIMING
-                    tm_iter += clock64() - t_it0;
-#endif
+                    __syncwarp();
+                    TADD(tm_issue)
                 }
-                if (elect_one()) {
-                    if (PAIR) mma2_commit_both(bar_chunk_full(seq & (NFULL - 1)));
-                    else mma_commit(bar_chunk_full(seq & (NFULL - 1)));
-                    if (C.layer == 0 && C.last_in_layer) {  // the prologue warp(s) may overwrite a0 once these MMAs are done
-                        if (PAIR) mma2_commit_both(bar_a0_free);
-                        else mma_commit(bar_a0_free);
-                    }
+                if (nis == 2) {  // pass the baton
+                    tc_fence_before();
+                    if (me == 0) asm volatile("bar.arrive 2, 64;\n" ::: "memory");
+                    else asm volatile("bar.arrive 3, 64;\n" ::: "memory");
                 }
-                __syncwarp();
-                ++seq;
+                // advance to this warp's next record
+                slot += nis;
+                if (slot >= nslots) {
+                    slot -= nslots;
+                    rphase ^= 1u;
+                }
+                it = it_n;
+                rec = nxt;
+                if (roll) {
+                    unit += ustep;
+                    if (unit >= nunits) break;
+                    tpar ^= 1u;
+                    first_tile = 0;
+                    seq_base += static_cast<uint32_t>(n_chunks);
+                }
             }
-        }
+            // the warp that did not issue the CTA's last record takes the last baton, so that no barrier is left half-arrived
+            if (nis == 2 && static_cast<uint32_t>(me) != last_owner) {
+                if (me == 0) asm volatile("bar.sync 3, 64;\n" ::: "memory");
+                else asm volatile("bar.sync 2, 64;\n" ::: "memory");
+            }
 #if VAE21_TC_TIMING
-        if (lane == 0 && blockIdx.x < 160) {
-            long long* o = g_tc_timing[blockIdx.x];
-            o[0] = clock64() - tm_total;
-            o[1] = tm_a0; o[2] = tm_q; o[3] = tm_ring; o[4] = tm_opnd; o[5] = tm_issue; o[6] = tm_iter;
-        }
+            if (lane == 0 && blockIdx.x < 160) {
+                long long* o = g_tc_timing[blockIdx.x] + 8 * me;
+                o[0] = clock64() - tm_total;
+                o[1] = tm_flag; o[2] = tm_ring; o[3] = tm_token; o[4] = tm_issue;
+            }
 #endif
+        }
     } else if (warp == 2 || warp == 3) {
         // ===================== prologue warps: layer-0 operand of every tile ===================
         // fused parameter transform (preprocess.py:74-78, :105-108) -> a0 (k padded to 16); role 2 takes rows 0..63, role 3 rows
-        // 64..127.  They run one tile ahead of the MMAs, off the epilogue warps' critical path.
+        // 64..127.  The operand words of the NEXT tile are computed first and held in registers; only then does the warp wait for
+        // the current tile's layer-0 MMAs to release a0 -- the parameter loads and the fp64 logarithms are off every critical path.
         const int K0 = P.K0;
         uint32_t nfree = 0;
 #pragma unroll 1
         for (long long unit = unit0; unit < nunits; unit += ustep, ++nfree) {
             const long long tile = CG * unit + rank;
+            uint32_t w[MT / 64][16];
+#pragma unroll
+            for (int rr = 0; rr < MT / 64; ++rr) {
+                float x[16];
+                prologue_row(a, nc, tile * MT + (warp - 2) * (MT / 2) + rr * 32 + lane, K0, x);
+                split16<FMT>(x, w[rr]);
+            }
             if (nfree > 0) mbar_wait(bar_a0_free, (nfree - 1u) & 1u);
-#pragma unroll 1
+#pragma unroll
             for (int rr = 0; rr < MT / 64; ++rr) {
                 const int row = (warp - 2) * (MT / 2) + rr * 32 + lane;
-                float x[16];
-                prologue_row(a, nc, tile * MT + row, K0, x);
-                uint32_t w[16];
-                split16<FMT>(x, w);
                 uint8_t* a0 = sm + P.off_a0;
-                *reinterpret_cast<uint4*>(a0 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-                *reinterpret_cast<uint4*>(a0 + A_KG_BYTES + row * 16) = make_uint4(w[4], w[5], w[6], w[7]);
-                *reinterpret_cast<uint4*>(a0 + 2 * A_KG_BYTES + row * 16) = make_uint4(w[8], w[9], w[10], w[11]);
-                *reinterpret_cast<uint4*>(a0 + 3 * A_KG_BYTES + row * 16) = make_uint4(w[12], w[13], w[14], w[15]);
+                *reinterpret_cast<uint4*>(a0 + row * 16) = make_uint4(w[rr][0], w[rr][1], w[rr][2], w[rr][3]);
+                *reinterpret_cast<uint4*>(a0 + A_KG_BYTES + row * 16) = make_uint4(w[rr][4], w[rr][5], w[rr][6], w[rr][7]);
+                *reinterpret_cast<uint4*>(a0 + 2 * A_KG_BYTES + row * 16) = make_uint4(w[rr][8], w[rr][9], w[rr][10], w[rr][11]);
+                *reinterpret_cast<uint4*>(a0 + 3 * A_KG_BYTES + row * 16) = make_uint4(w[rr][12], w[rr][13], w[rr][14], w[rr][15]);
             }
             fence_async_smem();
             __syncwarp();
@@ -1117,7 +1273,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 else mbar_arrive(bar_a0_ready);
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 4 + NEPI / 32) {
         // ===================== epilogue warps ================================================
         // thread = tile row = TMEM lane; the EPS warps that share a TMEM sub-partition split the 16-column groups of every
         // accumulator chunk (group g goes to warp share g mod EPS).
@@ -1386,6 +1542,15 @@ inline cudaError_t launch_om(const Plan& P, const NormConsts& nc, const LaunchAr
 inline cudaError_t launch(const Plan& P, const NormConsts& nc, const LaunchArgs& a, const void* wimg, const float* bias,
                           int fmt, int sm_count, cudaStream_t st) {
     if (a.n <= 0) return cudaSuccess;
+#ifdef VAE21_TC_DEV_FAST  // development builds: only the two pair kernels the A/B scripts run (compiles in a fraction of the time)
+    {
+        const long long nunits = (a.n + 2 * MT - 1) / (2 * MT);
+        const int grid = 2 * static_cast<int>(std::min<long long>(nunits, sm_count / 2));
+        if (a.out_mode == OUT_CHI2 || a.out_mode == OUT_ERROR || fmt == 1) return cudaErrorNotSupported;
+        return fmt == 0 ? launch_one<0, 2, OM_ROWS>(P, nc, a, static_cast<const uint8_t*>(wimg), bias, grid, st)
+                        : launch_one<2, 2, OM_ROWS>(P, nc, a, static_cast<const uint8_t*>(wimg), bias, grid, st);
+    }
+#else
     static const int cg_env = std::getenv("VAE21_TC_CTA_GROUP") ? std::atoi(std::getenv("VAE21_TC_CTA_GROUP")) : 0;
     const int cg = (cg_env == 1 || cg_env == 2) ? cg_env : P.default_cg;
     const uint8_t* w = static_cast<const uint8_t*>(wimg);
@@ -1399,10 +1564,19 @@ inline cudaError_t launch(const Plan& P, const NormConsts& nc, const LaunchArgs&
     const int grid = static_cast<int>(std::min<long long>(ntiles, sm_count));
     return fmt == 0 ? launch_om<0, 1>(P, nc, a, w, bias, grid, st)
            : fmt == 1 ? launch_om<1, 1>(P, nc, a, w, bias, grid, st) : launch_om<2, 1>(P, nc, a, w, bias, grid, st);
+#endif
 }
 
 #if VAE21_TC_TIMING
 inline cudaError_t read_timing(long long* host /*[160*16]*/) { return cudaMemcpyFromSymbol(host, g_tc_timing, sizeof(long long) * 160 * 16); }
+inline cudaError_t read_rec_timing(unsigned long long* host /*[3*256]*/, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(host, g_tc_rec, sizeof(unsigned long long) * 3 * 256);
+    if (e == cudaSuccess && reset) {
+        static unsigned long long zero[3 * 256] = {0};
+        e = cudaMemcpyToSymbol(g_tc_rec, zero, sizeof(zero));
+    }
+    return e;
+}
 #endif
 
 }  // namespace tck

@@ -756,6 +756,7 @@ int vae21_time_predict(vae21_handle* h, const void* params_dev, int params_dtype
 #if VAE21_TC_TIMING
 // profiling builds only (not declared in vae21.h)
 int vae21_debug_tc_timing(long long* out) { return tck::read_timing(out) == cudaSuccess ? 0 : 3; }
+int vae21_debug_tc_rec_timing(unsigned long long* out, int reset) { return tck::read_rec_timing(out, reset) == cudaSuccess ? 0 : 3; }
 
 #endif
 

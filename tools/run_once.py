@@ -26,6 +26,10 @@ emu = emu_mod.DirectEmulator(stats=pp.NormStats(pmin, pmax, mu, sd))
 emu.emulator = emu_mod.DenseModel(kh.DenseChainWeights(ks, bs, relu, name="emulator"))
 params = torch.from_numpy(rm.draw_params(rows, seed=1)).cuda()
 out = torch.empty((rows, 451), dtype=torch.float32, device="cuda")
+if os.environ.get("VAE21_RUN_NORMALISED"):  # bypass the parameter transform: already-normalised float32 inputs straight into the Dense chain
+    xn = torch.rand((rows, 7), dtype=torch.float32, device="cuda") * 2 - 1
+    _p = emu.emulator.predict
+    emu.predict = lambda _params, out=None, precision=None: _p(xn, out=out, precision=precision)
 for _ in range(launches):
     emu.predict(params, out=out, precision=prec)
 torch.cuda.synchronize()
