@@ -31,6 +31,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda.h>
 #include <cuda_fp8.h>
 
 #include <algorithm>
@@ -50,8 +51,9 @@ constexpr int MT = 128;
 #endif
 constexpr int EPS = VAE21_TC_EPI_PER_SUB;
 constexpr int NEPI = 128 * EPS;          // epilogue threads
-constexpr int NTHREADS = 160 + NEPI;     // roles: 0 producer, 1 MMA issuer A, 2-3 prologue, 4..4+NEPI/32-1 epilogue, last = MMA issuer B
-constexpr int WARP_ISSUER_B = 4 + NEPI / 32;  // role index of the second MMA-issuing warp (= its hardware warp)
+constexpr int NTHREADS = 128 + NEPI;     // roles: 0 producer, 1 MMA issuer A (follower CTA of a pair: ring forwarder), 2 prologue, 3 MMA issuer B, 4.. epilogue
+                                         // (a 21st warp would cost 16 registers per thread: the register file is allocated per 4 warps)
+constexpr int WARP_ISSUER_B = 3;  // role index of the second MMA-issuing warp
 constexpr int MAXL = 8;
 constexpr int MAXC = 32;
 constexpr int NFULL = 4;          // ring of "accumulator chunk ready" barriers
@@ -60,6 +62,10 @@ constexpr int NFULL = 4;          // ring of "accumulator chunk ready" barriers
                            // 16 no hi/lo split arithmetic, 32 no hidden-layer operand writes, 128 no weight ring at all (MMAs read stale smem)
 #endif
 constexpr int DBG = VAE21_TC_ABLATE;
+#ifndef VAE21_TC_STORE_DBG
+#define VAE21_TC_STORE_DBG 0  // profiling only (bit mask): 1 no box store issue, 2 no scalar stores around the boxes, 4 no wait for earlier boxes, 8 no barrier
+#endif
+constexpr int SDBG = VAE21_TC_STORE_DBG;
 #ifndef VAE21_TC_TIMING
 #define VAE21_TC_TIMING 0  // profiling only: per-CTA cycle counters of the MMA warp's waits (tools/tc_timing.py)
 #endif
@@ -112,6 +118,7 @@ struct Chunk {
     int src_first, src_count;   // chunks of the producing layer (first chunk of a layer > 0 only, else src_count = 0)
     float inv_s8;
     unsigned w_off;  // byte offset of the first stage in the weight image
+    int st_w, st_map;  // final-layer chunks, OM_ROWS: width of the chunk's tensor-store boxes (0: none) and which tensor map has that box
 };
 
 struct Plan {
@@ -130,6 +137,9 @@ struct Plan {
     int iter_off[2], n_iter[2];
     int l0_iters[2];             // ring slots of layer 0 (arrival count of the "a0 may be overwritten" barrier)
     int off_iter;                // shared-memory copy of the issue table
+    // output staging (OM_ROWS, see the epilogue): per buffer 16 arrays (TMEM sub-partition x row residue mod 4) of stage_sq bytes,
+    // each a dense [8 super-rows][box width] tile; 1 or 2 buffers; the distinct box widths (one tensor map each)
+    int stage_sq, stage_bufs, n_maps, map_w[4];
     // shared-memory carve-up (bytes from the 1024-aligned base)
     int off_act, off_stage, off_a0, off_ring, off_ring2, off_bias, off_s0, off_obs, off_isig, off_bar, smem_total;
     unsigned w_bytes;
@@ -415,17 +425,38 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
     // shared memory
     int off = 0;
     P.off_act = off;
-    const int stage_bytes = 4 * EPS * 32 * 20 * 4;  // output transpose staging of the epilogue warps
-    int act_bytes = std::max(smem_w / 16 * KSTEP_BYTES, stage_bytes);
-    // The staging tiles alias the activation buffer where the last layer does not read it: all of it when
-    // the last layer's operand is in TMEM, else the part above that operand (grown if needed).
-    if (P.L[last].a_src == A_SMEM_ACT) {
-        const int used = P.L[last].K / 16 * KSTEP_BYTES;
-        act_bytes = std::max(act_bytes, used + stage_bytes);
-        P.off_stage = off + used;
-    } else {
-        P.off_stage = off;
+    // Output staging (see the epilogue).  Box width of a final chunk: a multiple of 4 words that leaves room for the per-row shift
+    // (<= 3 columns) inside the chunk's valid columns, and = 12 (mod 16): with that pitch the 32 rows of a warp hit 32 different banks.
+    P.n_maps = 0;
+    int wmax = 0;
+    for (int c = P.L[last].first_chunk; c < nchunks; ++c) {
+        const int valid = std::min(P.C[c].ncols, P.n_out - P.C[c].n0);
+        int w = (valid - 3 >= 12) ? ((valid - 3 - 12) / 16 * 16 + 12) : 0;
+        int mi = -1;
+        for (int i = 0; i < P.n_maps; ++i)
+            if (P.map_w[i] == w) mi = i;
+        if (w > 0 && mi < 0) {
+            if (P.n_maps < 4) {
+                mi = P.n_maps;
+                P.map_w[P.n_maps++] = w;
+            } else {
+                w = 0;  // more than four distinct widths: this chunk is written with plain stores
+            }
+        }
+        P.C[c].st_w = w;
+        P.C[c].st_map = mi < 0 ? 0 : mi;
+        wmax = std::max(wmax, w);
     }
+    P.stage_sq = (8 * std::max(wmax, 12) * 4 + 127) / 128 * 128;
+    const int stage_buf_bytes = 16 * P.stage_sq;
+    // The staging buffers alias the activation buffer where the last layer does not read it: all of it when the last layer's operand
+    // is in TMEM, else the part above that operand (grown if needed).  Two buffers (one final chunk staged while the previous one is
+    // being read out) where the activation buffer is that large anyway, else one.
+    const int act_need = smem_w / 16 * KSTEP_BYTES;
+    const int used = (P.L[last].a_src == A_SMEM_ACT) ? P.L[last].K / 16 * KSTEP_BYTES : 0;
+    P.stage_bufs = (used + 2 * stage_buf_bytes <= std::max(act_need, 96 * 1024)) ? 2 : 1;
+    const int act_bytes = std::max(act_need, used + P.stage_bufs * stage_buf_bytes);
+    P.off_stage = off + used;
     off += act_bytes;
     P.off_a0 = off;
     off += KSTEP_BYTES;
@@ -447,9 +478,9 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
     P.off_ring2 = off2;
     // Even slot counts: with two issuing warps alternating slots, every use of a slot must be observed by the SAME warp (mbarrier
     // waits are by phase parity: a warp that saw only every other use of a slot would pass on a stale completion).
-    P.nslots = std::min(MAX_SLOTS, (SMEM_LIMIT - 128 /*alignment slack*/ - off1) / P.slot_bytes) & ~1;
-    if (P.nslots < 2) { why = "shared memory: activations leave no room for a weight ring"; return false; }
-    P.nslots2 = std::min(MAX_SLOTS, (SMEM_LIMIT - 128 - off2) / P.slot_bytes2) & ~1;
+    P.nslots = std::max(0, std::min(MAX_SLOTS, (SMEM_LIMIT - 128 /*alignment slack*/ - off1) / P.slot_bytes) & ~1);  // 0: no one-CTA variant
+    P.nslots2 = std::max(0, std::min(MAX_SLOTS, (SMEM_LIMIT - 128 - off2) / P.slot_bytes2) & ~1);
+    if (P.nslots2 < 2) { why = "shared memory: activations leave no room for a weight ring"; return false; }
     P.smem_total2 = off2 + P.nslots2 * P.slot_bytes2 + 128;
     P.smem_total = off1 + P.nslots * P.slot_bytes + 128;
     static const int issuers_env = std::getenv("VAE21_TC_ISSUERS") ? std::atoi(std::getenv("VAE21_TC_ISSUERS")) : 2;
@@ -538,14 +569,14 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
                        const int* relu, Plan& P, std::vector<unsigned short>* img, std::vector<float>& bias_img,
                        std::string& why) {
     std::string why_a, why_b;
-    if (build_plan_with(false, n_layers, dims, kernels, biases, relu, P, img, bias_img, why_a) && P.nslots >= 3) return true;
+    if (build_plan_with(false, n_layers, dims, kernels, biases, relu, P, img, bias_img, why_a) && P.nslots2 >= 4) return true;
     Plan Pa = P;
-    const bool ok_a = why_a.empty() && Pa.n_chunks > 0 && Pa.nslots >= 2;
+    const bool ok_a = why_a.empty() && Pa.n_chunks > 0 && Pa.nslots2 >= 2;
     std::vector<unsigned short> img_b[3];
     std::vector<float> bias_b;
     Plan Pb;
     const bool ok_b = build_plan_with(true, n_layers, dims, kernels, biases, relu, Pb, img_b, bias_b, why_b);
-    if (ok_b && (!ok_a || Pb.nslots > Pa.nslots)) {
+    if (ok_b && (!ok_a || Pb.nslots2 > Pa.nslots2)) {
         P = Pb;
         for (int f = 0; f < 3; ++f) img[f].swap(img_b[f]);
         bias_img.swap(bias_b);
@@ -794,20 +825,24 @@ __device__ __forceinline__ float fmax3_abs(float a, float b, float c) {
     return r;
 }
 
-// Split two fp32 values into packed 16-bit hi and lo words (element 0 in the low half).
+// Split two fp32 values into packed 16-bit hi and lo words (element 0 in the low half).  The remainders v - hi are exact in fp32
+// and computed as ONE packed fma (fma.rn.f32x2 on sm_100: two independent IEEE fmas, hi * (-1) + v) -- the epilogue is bound by
+// its instruction count.
 template <int FMT>
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const float2 v = make_float2(a, b), m1 = make_float2(-1.f, -1.f);
     if (FMT == 0) {
         __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
         hi = *reinterpret_cast<uint32_t*>(&h);
-        const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
-        __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+        const float2 hf = make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
+        const float2 d = __ffma2_rn(hf, m1, v);
+        __nv_bfloat162 l = __floats2bfloat162_rn(d.x, d.y);
         lo = *reinterpret_cast<uint32_t*>(&l);
     } else {
         __half2 h = __floats2half2_rn(a, b);
         hi = *reinterpret_cast<uint32_t*>(&h);
-        const float2 hf = __half22float2(h);
-        __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+        const float2 d = __ffma2_rn(__half22float2(h), m1, v);
+        __half2 l = __floats2half2_rn(d.x, d.y);
         lo = *reinterpret_cast<uint32_t*>(&l);
     }
 }
@@ -820,12 +855,15 @@ __device__ __forceinline__ void split4_f8(float v0, float v1, float v2, float v3
     const __half2 ha = __floats2half2_rn(v0, v1), hb = __floats2half2_rn(v2, v3);
     h01 = *reinterpret_cast<const uint32_t*>(&ha);
     h23 = *reinterpret_cast<const uint32_t*>(&hb);
-    const float2 fa = __half22float2(ha), fb = __half22float2(hb);
     const uint32_t p0 = __nv_cvt_float2_to_fp8x2(make_float2(v0, v1), __NV_SATFINITE, __NV_E4M3);
     const uint32_t p1 = __nv_cvt_float2_to_fp8x2(make_float2(v2, v3), __NV_SATFINITE, __NV_E4M3);
     b_hi8 = p0 | (p1 << 16);
-    const uint32_t q0 = __nv_cvt_float2_to_fp8x2(make_float2((v0 - fa.x) * A_LO_SCALE, (v1 - fa.y) * A_LO_SCALE), __NV_SATFINITE, __NV_E4M3);
-    const uint32_t q1 = __nv_cvt_float2_to_fp8x2(make_float2((v2 - fb.x) * A_LO_SCALE, (v3 - fb.y) * A_LO_SCALE), __NV_SATFINITE, __NV_E4M3);
+    // (v - hi) * 2^11: both steps exact in fp32, two packed instructions per pair
+    const float2 m1 = make_float2(-1.f, -1.f), sc = make_float2(A_LO_SCALE, A_LO_SCALE);
+    const float2 da = __fmul2_rn(__ffma2_rn(__half22float2(ha), m1, make_float2(v0, v1)), sc);
+    const float2 db = __fmul2_rn(__ffma2_rn(__half22float2(hb), m1, make_float2(v2, v3)), sc);
+    const uint32_t q0 = __nv_cvt_float2_to_fp8x2(da, __NV_SATFINITE, __NV_E4M3);
+    const uint32_t q1 = __nv_cvt_float2_to_fp8x2(db, __NV_SATFINITE, __NV_E4M3);
     b_lo8 = q0 | (q1 << 16);
 }
 // 16 consecutive features of one row -> the 16 operand words of a k-step: w[0..7] = 16-bit hi pairs (k-groups 0 and 1),
@@ -912,6 +950,47 @@ __device__ __noinline__ void prologue_row(const LaunchArgs& a, const NormConsts&
     }
 }
 
+// The same for a compile-time parameter count (the emulators have 7): everything unrolled, so the normalisation constants are
+// immediate constant-bank operands and the row's values stay in registers -- the generic version above indexes the constant bank and
+// a local array dynamically, which made one 32-row round cost ~14k cycles (round-2 measurement) and the lone prologue warp the
+// kernel's bottleneck.  The double-precision log10 stays one out-of-line copy.
+__device__ __noinline__ double log10_f64(double p) { return log10(p); }
+
+template <int K0>
+__device__ __forceinline__ void prologue_row_fixed(const LaunchArgs& a, const NormConsts& nc, long long grow, float (&x)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = 0.f;
+    if (grow >= a.n) return;
+    const bool f32_in = (a.in_mode == IN_PARAMS_F32);
+    double pv[K0];
+    if (f32_in) {
+#pragma unroll
+        for (int j = 0; j < K0; ++j) pv[j] = static_cast<double>(reinterpret_cast<const float*>(a.in)[grow * K0 + j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < K0; ++j) pv[j] = reinterpret_cast<const double*>(a.in)[grow * K0 + j];
+    }
+#pragma unroll
+    for (int j = 0; j < K0; ++j) {
+        double p = pv[j];
+        if (j == nc.floor_col && p == 0.0) p = f32_in ? static_cast<double>(static_cast<float>(nc.floor_val)) : nc.floor_val;
+        double t = p;
+        if (nc.log_mask[j]) {
+            t = log10_f64(p);
+            if (f32_in) t = static_cast<double>(static_cast<float>(t));  // numpy takes the log of a float32 array in float32
+        }
+        x[j] = static_cast<float>(fma(t - nc.pmin[j], nc.pscale[j], -1.0));
+    }
+}
+
+// Tensor maps of the output for the OM_ROWS store path (encoded per launch on the host, see make_store_maps): the (n, n_out) float32
+// output viewed as [n / 4 super-rows][4 n_out words] -- a row pitch of 4 n_out bytes x 4 is a multiple of 16 bytes for ANY n_out,
+// which a tensor map requires and the 1804-byte rows of the 451-bin spectra are not -- one map per distinct box width.
+struct alignas(64) StoreMaps {
+    CUtensorMap m[4];
+    long long rows4;  // 4 * (n / 4): rows covered by complete super-rows (0: tensor stores off for this launch)
+};
+
 // Output modes as a template parameter (each instantiation carries only its own final-layer code):
 enum : int { OM_ROWS = 0 /* OUT_PREDICT / OUT_NORMALISED: spectra written */, OM_CHI2 = 1, OM_ERROR = 2 };
 
@@ -925,7 +1004,7 @@ __device__ __forceinline__ constexpr float sat_limit() { return FMT == 2 ? 480.f
 template <int FMT, int CG, int OM>  // FMT 0: bf16 split (3 MMAs per k-step), 1: fp16 split (3), 2: fp16 + e4m3 corrections (2)
 __global__ void __launch_bounds__(NTHREADS, 1)
 vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormConsts nc, const __grid_constant__ LaunchArgs a,
-                const uint8_t* __restrict__ wimg, const float* __restrict__ bias_g) {
+                const uint8_t* __restrict__ wimg, const float* __restrict__ bias_g, const __grid_constant__ StoreMaps smaps) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 127u) & ~127u;  // shared-window address of the carve-up
@@ -939,7 +1018,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
     const int tid = threadIdx.x, lane = tid & 31;
     const int hw_warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 #if VAE21_TC_CTRL_LAST
-    const int warp = hw_warp < NEPI / 32 ? hw_warp + 4 : (hw_warp < NEPI / 32 + 4 ? hw_warp - NEPI / 32 : hw_warp);
+    const int warp = hw_warp < NEPI / 32 ? hw_warp + 4 : hw_warp - NEPI / 32;
 #else
     const int warp = hw_warp;
 #endif
@@ -981,7 +1060,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         for (int i = 0; i < NFULL; ++i) mbar_init(bar_chunk_full(i), 2);  // the commits behind the last two ring slots of a chunk
         for (int b = 0; b < 2; ++b) mbar_init(bar_q_empty(b), (NEPI / 32) * both);
         for (int j = 0; j < MAX_LCHUNK; ++j) mbar_init(bar_act_ready(j), (NEPI / 32) * both);
-        mbar_init(bar_a0_ready, 2 * both);  // one arrival from each of the two prologue warps (of each CTA)
+        mbar_init(bar_a0_ready, both);  // one arrival from the prologue warp (of each CTA)
         mbar_init(bar_a0_free, static_cast<uint32_t>(P.l0_iters[PAIR ? 1 : 0]));  // one commit behind every ring slot of layer 0
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -1239,32 +1318,71 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
             }
 #endif
         }
-    } else if (warp == 2 || warp == 3) {
-        // ===================== prologue warps: layer-0 operand of every tile ===================
-        // fused parameter transform (preprocess.py:74-78, :105-108) -> a0 (k padded to 16); role 2 takes rows 0..63, role 3 rows
-        // 64..127.  The operand words of the NEXT tile are computed first and held in registers; only then does the warp wait for
-        // the current tile's layer-0 MMAs to release a0 -- the parameter loads and the fp64 logarithms are off every critical path.
+    } else if (warp == 2) {
+        // ===================== prologue warp: layer-0 operand of every tile ====================
+        // fused parameter transform (preprocess.py:74-78, :105-108) -> a0 (k padded to 16), four rounds of 32 rows.  With at most 8
+        // input parameters (the emulators have 7) the operand words of the NEXT tile are computed first and held in registers (8
+        // words per row: only the first k-group of a0 is ever non-zero), and only then does the warp wait for the current tile's
+        // layer-0 MMAs to release a0 -- parameter loads and fp64 logarithms are off every critical path.  Wider inputs: after the wait.
         const int K0 = P.K0;
+        uint8_t* const a0 = sm + P.off_a0;
+        for (int i = lane; i < KSTEP_BYTES / 16; i += 32) reinterpret_cast<uint4*>(a0)[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
         uint32_t nfree = 0;
 #pragma unroll 1
         for (long long unit = unit0; unit < nunits; unit += ustep, ++nfree) {
             const long long tile = CG * unit + rank;
-            uint32_t w[MT / 64][16];
+#if VAE21_TC_TIMING
+            const long long tp0 = clock64();
+#endif
+            if (K0 <= 8) {
+                uint32_t w8[MT / 32][8];
 #pragma unroll
-            for (int rr = 0; rr < MT / 64; ++rr) {
-                float x[16];
-                prologue_row(a, nc, tile * MT + (warp - 2) * (MT / 2) + rr * 32 + lane, K0, x);
-                split16<FMT>(x, w[rr]);
-            }
-            if (nfree > 0) mbar_wait(bar_a0_free, (nfree - 1u) & 1u);
+                for (int rr = 0; rr < MT / 32; ++rr) {
+                    float x[16];
+                    if (K0 == 7 && (a.in_mode == IN_PARAMS_F64 || a.in_mode == IN_PARAMS_F32)) prologue_row_fixed<7>(a, nc, tile * MT + rr * 32 + lane, x);
+                    else prologue_row(a, nc, tile * MT + rr * 32 + lane, K0, x);
+                    uint32_t w[16];
+                    split16<FMT>(x, w);
+                    w8[rr][0] = w[0]; w8[rr][1] = w[1]; w8[rr][2] = w[2]; w8[rr][3] = w[3];
+                    if (FMT == 2) { w8[rr][4] = w[8]; w8[rr][5] = w[9]; w8[rr][6] = w[12]; w8[rr][7] = w[13]; }
+                    else { w8[rr][4] = w[8]; w8[rr][5] = w[9]; w8[rr][6] = w[10]; w8[rr][7] = w[11]; }
+                }
+#if VAE21_TC_TIMING
+                const long long tp1 = clock64();
+#endif
+                if (nfree > 0) mbar_wait(bar_a0_free, (nfree - 1u) & 1u);
+#if VAE21_TC_TIMING
+                if (lane == 0 && blockIdx.x < 160) {
+                    g_tc_timing[blockIdx.x][5] += tp1 - tp0;        // operand computation
+                    g_tc_timing[blockIdx.x][6] += clock64() - tp1;  // wait for a0 to be released
+                }
+#endif
 #pragma unroll
-            for (int rr = 0; rr < MT / 64; ++rr) {
-                const int row = (warp - 2) * (MT / 2) + rr * 32 + lane;
-                uint8_t* a0 = sm + P.off_a0;
-                *reinterpret_cast<uint4*>(a0 + row * 16) = make_uint4(w[rr][0], w[rr][1], w[rr][2], w[rr][3]);
-                *reinterpret_cast<uint4*>(a0 + A_KG_BYTES + row * 16) = make_uint4(w[rr][4], w[rr][5], w[rr][6], w[rr][7]);
-                *reinterpret_cast<uint4*>(a0 + 2 * A_KG_BYTES + row * 16) = make_uint4(w[rr][8], w[rr][9], w[rr][10], w[rr][11]);
-                *reinterpret_cast<uint4*>(a0 + 3 * A_KG_BYTES + row * 16) = make_uint4(w[rr][12], w[rr][13], w[rr][14], w[rr][15]);
+                for (int rr = 0; rr < MT / 32; ++rr) {
+                    const int row = rr * 32 + lane;
+                    *reinterpret_cast<uint4*>(a0 + row * 16) = make_uint4(w8[rr][0], w8[rr][1], w8[rr][2], w8[rr][3]);
+                    if (FMT == 2) {  // second tile: k-group 0 = e4m3(x) of the 16 k, k-group 1 = e4m3 of the scaled remainders
+                        *reinterpret_cast<uint2*>(a0 + 2 * A_KG_BYTES + row * 16) = make_uint2(w8[rr][4], w8[rr][5]);
+                        *reinterpret_cast<uint2*>(a0 + 3 * A_KG_BYTES + row * 16) = make_uint2(w8[rr][6], w8[rr][7]);
+                    } else {
+                        *reinterpret_cast<uint4*>(a0 + 2 * A_KG_BYTES + row * 16) = make_uint4(w8[rr][4], w8[rr][5], w8[rr][6], w8[rr][7]);
+                    }
+                }
+            } else {
+                if (nfree > 0) mbar_wait(bar_a0_free, (nfree - 1u) & 1u);
+#pragma unroll 1
+                for (int rr = 0; rr < MT / 32; ++rr) {
+                    const int row = rr * 32 + lane;
+                    float x[16];
+                    prologue_row(a, nc, tile * MT + row, K0, x);
+                    uint32_t w[16];
+                    split16<FMT>(x, w);
+                    *reinterpret_cast<uint4*>(a0 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(a0 + A_KG_BYTES + row * 16) = make_uint4(w[4], w[5], w[6], w[7]);
+                    *reinterpret_cast<uint4*>(a0 + 2 * A_KG_BYTES + row * 16) = make_uint4(w[8], w[9], w[10], w[11]);
+                    *reinterpret_cast<uint4*>(a0 + 3 * A_KG_BYTES + row * 16) = make_uint4(w[12], w[13], w[14], w[15]);
+                }
             }
             fence_async_smem();
             __syncwarp();
@@ -1273,22 +1391,40 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 else mbar_arrive(bar_a0_ready);
             }
         }
-    } else if (warp >= 4 && warp < 4 + NEPI / 32) {
+    } else if (warp >= 4) {
         // ===================== epilogue warps ================================================
         // thread = tile row = TMEM lane; the EPS warps that share a TMEM sub-partition split the 16-column groups of every
-        // accumulator chunk (group g goes to warp share g mod EPS).
+        // accumulator chunk into EPS contiguous ranges (warp share h takes groups [ng h / EPS, ng (h + 1) / EPS)).
         const int ew = warp - 4;
         const int half = ew >> 2;                 // which share of the 16-column groups
         const int sub = warp & 3;                 // TMEM sub-partition this warp may access
         const int row = sub * 32 + lane;          // tile row == TMEM lane
         const uint32_t tlane = static_cast<uint32_t>(sub * 32) << 16;
-        float* stage = reinterpret_cast<float*>(sm + P.off_stage) + ew * (32 * 20);
         const int NO = P.n_out;
         uint32_t seq = 0;
         uint32_t tcount = 0;
+        uint32_t fin_cnt = 0;  // final-layer chunks staged so far (staging buffer parity)
         float vmax = 0.f;  // largest hidden activation this thread converted (operand-range check, FMT 1 / 2)
+        // OM_ROWS output path.  The 1804-byte rows of the (n, 451) output rule out a row-pitched tensor map (pitch must be a multiple
+        // of 16 bytes) and make plain stores expensive (round-2 ablation: the transposes + 64-byte-segment STGs of round 1 cost
+        // 0.31 ms of a 1.73 ms launch, one 1-D bulk store per thread and chunk 0.45 ms).  But FOUR rows are 7216 bytes: the output is
+        // a [n / 4][4 n_out] tensor whose "super-row" r4 holds rows 4 r4 .. 4 r4 + 3, and the chunk's columns of all rows with the
+        // same residue q = row mod 4 form a box -- if the box starts at a 16-byte boundary, i.e. if rows of residue q start `shift`
+        // = (-q n_out) mod 4 columns into the chunk.  So every thread stages the columns [shift, shift + W) of its row's chunk piece
+        // in the dense [8 super-rows][W] tile of its (sub-partition, residue) -- W = 12 (mod 16) makes the 32 rows of a warp hit 32
+        // different banks --, writes the <= 3 + 4 columns around it with scalar stores straight from registers, and after one
+        // named barrier of the sub-partition's four warps FOUR lanes issue the four box stores (cp.async.bulk.tensor.2d): 16 store
+        // instructions per chunk and CTA instead of 2048.  Two staging buffers alternate between final chunks; the issuing lanes wait
+        // for the boxes of earlier chunks to have been read before they enter the next barrier, which frees the older buffer for
+        // everybody.  Rows beyond the last complete super-row, launches with an unaligned output and chunks without a box are
+        // written with plain stores.
+        const int q_res = row & 3;                                    // row residue (tile bases are multiples of 4)
+        const int shift = (4 - ((q_res * NO) & 3)) & 3;
+        const bool tma_launch = (OM == OM_ROWS) && smaps.rows4 > 0;
+        uint8_t* const stage_base = sm + P.off_stage + (sub * 4 + q_res) * P.stage_sq;
+        const bool issuer = (half == 0 && lane < 4);                  // lane q issues the box of residue q
 
-        // hand-off to the MMA issuer, which lives in the leader CTA of a pair
+        // hand-off to the MMA issuers, which live in the leader CTA of a pair
         auto signal_mma = [&](uint32_t bar) {
             if (PAIR && !leader) mbar_arrive_remote(bar, 0);
             else mbar_arrive(bar);
@@ -1298,11 +1434,6 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         for (long long unit = unit0; unit < nunits; unit += ustep, ++tcount) {
             const long long tile = CG * unit + rank;
             const long long grow = tile * MT + row;
-            const bool full_tile = (tile * MT + MT <= a.n);
-            // OM_ROWS: every store instruction of the final layer writes two 64-byte row segments -- lanes 0..15 the 16 columns of
-            // staged row R, lanes 16..31 those of row R + 4 (20-float staging rows: 4 rows apart = 16 banks apart, conflict-free)
-            const int cl = lane & 15, rsel = lane >> 4;
-            const long long orow0 = tile * MT + sub * 32 + 4 * rsel;
             float chi = 0.f, amp = 0.f;
 #pragma unroll 1
             for (int c = 0; c < n_chunks; ++c) {
@@ -1315,39 +1446,58 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 mbar_wait(bar_chunk_full(seq & (NFULL - 1)), (seq / NFULL) & 1u);
                 ++seq;
                 tc_fence_after();
+                if (OM == OM_ROWS && c == 0 && tcount > 0) {
+                    // the output staging buffers alias the activation buffer: before this tile's first activations are written, the box
+                    // stores of the previous tile must have read them
+                    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+                    asm volatile("bar.sync 1, %0;\n" ::"n"(NEPI) : "memory");
+                }
                 const float* bl = s_bias + c_bias_n0;
                 const int ng = c_ncols / 16;
+                const int g_lo = (ng * half) / EPS, g_hi = (ng * (half + 1)) / EPS;
                 const uint32_t tbase = tm + tlane + static_cast<uint32_t>(c_dcol);
+                // this chunk's tensor-store box (final layer, OM_ROWS): width st_w, this thread's row of the staging tile
+                const int st_w = (OM == OM_ROWS && out_dst == DST_FINAL && tma_launch) ? C.st_w : 0;
+                const bool staged = st_w > 0 && grow < smaps.rows4;  // else: plain stores
+                float* sstage = nullptr;  // word `col` of the chunk goes to sstage[col] for shift <= col < shift + st_w
+                if (OM == OM_ROWS && out_dst == DST_FINAL && tma_launch && P.stage_bufs == 1) {
+                    // a single staging buffer: the previous chunk's boxes must have been read before anybody overwrites it
+                    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+                    asm volatile("bar.sync %0, 128;\n" ::"r"(4 + sub) : "memory");
+                }
+                if (OM == OM_ROWS && out_dst == DST_FINAL) {
+                    sstage = reinterpret_cast<float*>(stage_base + ((P.stage_bufs == 2) ? (fin_cnt & 1u) * (16 * P.stage_sq) : 0)) + (lane >> 2) * st_w - shift;
+                    ++fin_cnt;
+                }
                 // group body (instantiated twice: the accumulator reads are software-pipelined over two register sets, so the load of
                 // this warp's next group is in flight while the current one is converted)
                 auto process = [&](uint32_t (&r)[16], int g) {
                     float v[16];
-                        if (out_dst != DST_FINAL) {
+                    if (out_dst != DST_FINAL) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float4 b4 = *reinterpret_cast<const float4*>(bl + 16 * g + 4 * q);
                             if (FMT == 2) {  // accumulators carry the weight scale S_l
-                                v[4 * q + 0] = fmaf(__uint_as_float(r[4 * q + 0]), inv_s8, b4.x);
-                                v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), inv_s8, b4.y);
-                                v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), inv_s8, b4.z);
-                                v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), inv_s8, b4.w);
+                                const float2 sc = make_float2(inv_s8, inv_s8);
+                                const float2 lo2 = __ffma2_rn(make_float2(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1])), sc, make_float2(b4.x, b4.y));
+                                const float2 hi2 = __ffma2_rn(make_float2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])), sc, make_float2(b4.z, b4.w));
+                                v[4 * q + 0] = lo2.x; v[4 * q + 1] = lo2.y; v[4 * q + 2] = hi2.x; v[4 * q + 3] = hi2.y;
                             } else {
-                                v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x;
-                                v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
-                                v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
-                                v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
+                                const float2 lo2 = __fadd2_rn(make_float2(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1])), make_float2(b4.x, b4.y));
+                                const float2 hi2 = __fadd2_rn(make_float2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])), make_float2(b4.z, b4.w));
+                                v[4 * q + 0] = lo2.x; v[4 * q + 1] = lo2.y; v[4 * q + 2] = hi2.x; v[4 * q + 3] = hi2.y;
                             }
                         }
                     } else {
                         const int n = c_n0 + 16 * g;
                         const float s1 = ((a.out_mode == OUT_NORMALISED) ? 1.f : nc.sd) * inv_s8;
+                        const float2 sc = make_float2(s1, s1);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float4 s4 = *reinterpret_cast<const float4*>(s_s0 + n + 4 * q);
-                            v[4 * q + 0] = fmaf(__uint_as_float(r[4 * q + 0]), s1, s4.x);
-                            v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), s1, s4.y);
-                            v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), s1, s4.z);
-                            v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), s1, s4.w);
+                            const float2 lo2 = __ffma2_rn(make_float2(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1])), sc, make_float2(s4.x, s4.y));
+                            const float2 hi2 = __ffma2_rn(make_float2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])), sc, make_float2(s4.z, s4.w));
+                            v[4 * q + 0] = lo2.x; v[4 * q + 1] = lo2.y; v[4 * q + 2] = hi2.x; v[4 * q + 3] = hi2.y;
                         }
                     }
                     if (out_dst != DST_FINAL) {
@@ -1394,45 +1544,53 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                             amp = fmaxf(amp, fabsf(t) * s_isig[n + i]);
                         }
                     } else if (!(DBG & 8)) {
-                        // 32x16 transpose through this warp's staging tile (row stride 20 floats: conflict-free 128-bit writes)
-                        const int n = c_n0 + 16 * g;
-                        float4* st4 = reinterpret_cast<float4*>(stage + lane * 20);
-                        st4[0] = make_float4(v[0], v[1], v[2], v[3]);
-                        st4[1] = make_float4(v[4], v[5], v[6], v[7]);
-                        st4[2] = make_float4(v[8], v[9], v[10], v[11]);
-                        st4[3] = make_float4(v[12], v[13], v[14], v[15]);
-                        __syncwarp();
-                        const float* sp = stage + (4 * rsel) * 20 + cl;
-                        float* op = a.out + orow0 * static_cast<long long>(NO) + n + cl;
-                        if (full_tile && n + 16 <= NO) {
+                        const int col0 = 16 * g;  // column of v[0] within the chunk
+                        float* op = a.out + grow * static_cast<long long>(NO) + c_n0;
+                        if (staged && col0 >= shift && col0 + 16 <= shift + st_w) {  // inside the box: stage
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {  // staged rows R = (i & 3) + 8 (i >> 2) and R + 4
-                                const int R = (i & 3) + 8 * (i >> 2);
-                                __stcs(op + static_cast<long long>(R) * NO, sp[R * 20]);
-                            }
-                        } else {
-#pragma unroll 1
+                            for (int i = 0; i < 16; ++i) sstage[col0 + i] = v[i];
+                        } else if (grow < a.n) {  // box boundary (or no box): stage what belongs to the box, store the rest
+#pragma unroll
                             for (int i = 0; i < 16; ++i) {
-                                const int R = (i & 3) + 8 * (i >> 2);
-                                if (orow0 + R < a.n && n + cl < NO) __stcs(op + static_cast<long long>(R) * NO, sp[R * 20]);
+                                const int col = col0 + i;
+                                if (staged && col >= shift && col < shift + st_w) sstage[col] = v[i];
+                                else if (c_n0 + col < NO && !(SDBG & 2)) __stcs(op + col, v[i]);
                             }
                         }
-                        __syncwarp();
                     }
                 };
-                if (half < ng && !(DBG & 2)) {
+                if (g_lo < g_hi && !(DBG & 2)) {
                     uint32_t ra[16], rb[16];
-                    tmem_ld16(tbase + static_cast<uint32_t>(16 * half), ra);
+                    tmem_ld16(tbase + static_cast<uint32_t>(16 * g_lo), ra);
 #pragma unroll 1
-                    for (int g = half; g < ng; g += 2 * EPS) {
+                    for (int g = g_lo; g < g_hi; g += 2) {
                         tmem_ld_wait();
-                        if (g + EPS < ng) tmem_ld16(tbase + static_cast<uint32_t>(16 * (g + EPS)), rb);
+                        if (g + 1 < g_hi) tmem_ld16(tbase + static_cast<uint32_t>(16 * (g + 1)), rb);
                         process(ra, g);
-                        if (g + EPS < ng) {
+                        if (g + 1 < g_hi) {
                             tmem_ld_wait();
-                            if (g + 2 * EPS < ng) tmem_ld16(tbase + static_cast<uint32_t>(16 * (g + 2 * EPS)), ra);
-                            process(rb, g + EPS);
+                            if (g + 2 < g_hi) tmem_ld16(tbase + static_cast<uint32_t>(16 * (g + 2)), ra);
+                            process(rb, g + 1);
                         }
+                    }
+                }
+                if (OM == OM_ROWS && out_dst == DST_FINAL && tma_launch && !(DBG & (2 | 8))) {
+                    fence_async_smem();  // the staged words are read by the async proxy
+                    // earlier chunks' boxes have been read: behind the barrier everybody may overwrite the OTHER staging buffer
+                    if (issuer && !(SDBG & 4)) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+                    if (!(SDBG & 8)) asm volatile("bar.sync %0, 128;\n" ::"r"(4 + sub) : "memory");
+                    if (issuer) {
+                        const long long r4 = (tile * MT) / 4 + 8 * sub;  // first super-row of this sub-partition
+                        const int sh = (4 - ((lane * NO) & 3)) & 3;     // this lane issues the box of residue `lane`
+                        if (st_w > 0 && 4 * r4 < smaps.rows4 && !(SDBG & 1)) {
+                            const uint32_t src = smem_u32(sm + P.off_stage + ((P.stage_bufs == 2) ? ((fin_cnt - 1u) & 1u) * (16 * P.stage_sq) : 0) +
+                                                          (sub * 4 + lane) * P.stage_sq);
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(
+                                             reinterpret_cast<uint64_t>(&smaps.m[C.st_map])),
+                                         "r"(lane * NO + c_n0 + sh), "r"(static_cast<int>(r4)), "r"(src)
+                                         : "memory");
+                        }
+                        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
                     }
                 }
                 // publish: operand visible to the tensor pipe / accumulator buffer free
@@ -1445,43 +1603,45 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                     if (out_dst != DST_FINAL) signal_mma(bar_act_ready(c_idx));
                 }
             }
-            // tile end: all epilogue warps meet (the output staging tiles alias the activation buffer, and the
-            // column shares of a row combine their chi^2 partials here)
-            float* chi_buf = s_chi + (tcount & 1u) * (EPS - 1) * 128;
-            float* amp_buf = s_amp + (tcount & 1u) * (EPS - 1) * 128;
-            if ((OM == OM_CHI2 || OM == OM_ERROR) && half > 0) chi_buf[(half - 1) * 128 + row] = chi;
-            if (OM == OM_ERROR && half > 0) amp_buf[(half - 1) * 128 + row] = amp;
-            asm volatile("bar.sync 1, %0;\n" ::"n"(NEPI) : "memory");
-            if (OM == OM_ERROR && half == 0) {
+            if (OM == OM_CHI2 || OM == OM_ERROR) {
+                // tile end: the column shares of a row combine their chi^2 partials
+                float* chi_buf = s_chi + (tcount & 1u) * (EPS - 1) * 128;
+                float* amp_buf = s_amp + (tcount & 1u) * (EPS - 1) * 128;
+                if (half > 0) chi_buf[(half - 1) * 128 + row] = chi;
+                if (OM == OM_ERROR && half > 0) amp_buf[(half - 1) * 128 + row] = amp;
+                asm volatile("bar.sync 1, %0;\n" ::"n"(NEPI) : "memory");
+                if (OM == OM_ERROR && half == 0) {
 #pragma unroll
-                for (int hh = 0; hh < EPS - 1; ++hh) {
-                    chi += chi_buf[hh * 128 + row];
-                    amp = fmaxf(amp, amp_buf[hh * 128 + row]);
-                }
-                if (grow < a.n) {
-                    float e = sqrtf(chi * a.err_inv_count);
-                    if (a.err_relative) e = e / amp * 100.f;
-                    a.chi2[grow] = e;
-                }
-            }
-            if (OM == OM_CHI2 && half == 0) {
-#pragma unroll
-                for (int hh = 0; hh < EPS - 1; ++hh) chi += chi_buf[hh * 128 + row];
-                unsigned long long key = ~0ull;
-                if (grow < a.n) {
-                    if (a.chi2) a.chi2[grow] = chi;
-                    key = pack_min_key(chi, static_cast<unsigned long long>(a.row_base + grow));
-                }
-                if (a.argmin_key) {
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-                        key = other < key ? other : key;
+                    for (int hh = 0; hh < EPS - 1; ++hh) {
+                        chi += chi_buf[hh * 128 + row];
+                        amp = fmaxf(amp, amp_buf[hh * 128 + row]);
                     }
-                    if (lane == 0 && key != ~0ull) atomicMin(a.argmin_key, key);
+                    if (grow < a.n) {
+                        float e = sqrtf(chi * a.err_inv_count);
+                        if (a.err_relative) e = e / amp * 100.f;
+                        a.chi2[grow] = e;
+                    }
+                }
+                if (OM == OM_CHI2 && half == 0) {
+#pragma unroll
+                    for (int hh = 0; hh < EPS - 1; ++hh) chi += chi_buf[hh * 128 + row];
+                    unsigned long long key = ~0ull;
+                    if (grow < a.n) {
+                        if (a.chi2) a.chi2[grow] = chi;
+                        key = pack_min_key(chi, static_cast<unsigned long long>(a.row_base + grow));
+                    }
+                    if (a.argmin_key) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                            key = other < key ? other : key;
+                        }
+                        if (lane == 0 && key != ~0ull) atomicMin(a.argmin_key, key);
+                    }
                 }
             }
         }
+        if (OM == OM_ROWS && issuer) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // all box stores complete before the CTA exits
         // operand-range check (FMT 1: fp16 hi/lo overflow beyond 65504; FMT 2: the e4m3 correction operands clip at 448): count the
         // epilogue threads that converted a hidden activation beyond the range.  fmaxf ignores NaN, so the reference's NaN
         // propagation for non-positive parameters does not count.
@@ -1504,7 +1664,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
 
 template <int FMT, int CG, int OM>
 inline cudaError_t launch_one(const Plan& P, const NormConsts& nc, const LaunchArgs& a, const uint8_t* wimg, const float* bias,
-                              int grid, cudaStream_t st) {
+                              int grid, cudaStream_t st, const StoreMaps& smaps) {
     static unsigned long long prepared = 0;  // per instantiation: bit d = the shared-memory attribute is set on device d
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1525,17 +1685,62 @@ inline cudaError_t launch_one(const Plan& P, const NormConsts& nc, const LaunchA
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, vae21_tc_kernel<FMT, CG, OM>, P, nc, a, wimg, bias);
+    return cudaLaunchKernelEx(&cfg, vae21_tc_kernel<FMT, CG, OM>, P, nc, a, wimg, bias, smaps);
 }
 
 inline cudaError_t prepare() { return cudaSuccess; }  // attributes are set per instantiation on first launch (launch_one)
 
+// Tensor maps for the OM_ROWS store path of one launch (see StoreMaps).  Leaves rows4 = 0 -- plain stores -- when the output is not
+// 16-byte aligned, has fewer than 4 rows, or the driver entry point is missing.  Maps are cached per (output pointer, rows, plan
+// widths): the host pipeline re-uses three device buffers, benchmark loops one.
+inline void make_store_maps(const Plan& P, const LaunchArgs& a, StoreMaps& sm) {
+    std::memset(&sm, 0, sizeof(sm));
+    if (a.out_mode == OUT_CHI2 || a.out_mode == OUT_ERROR || !a.out || P.n_maps == 0) return;
+    if ((reinterpret_cast<uintptr_t>(a.out) & 15u) || a.n < 4) return;
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) fn = nullptr;
+        return reinterpret_cast<encode_fn>(fn);
+    }();
+    if (!encode) return;
+    struct Entry { const float* out; long long n; int n_out, n_maps, w[4]; StoreMaps sm; };
+    static thread_local Entry cache[8];
+    static thread_local int next = 0;
+    for (const Entry& e : cache)
+        if (e.out == a.out && e.n == a.n && e.n_out == P.n_out && e.n_maps == P.n_maps && std::memcmp(e.w, P.map_w, sizeof(e.w)) == 0) {
+            sm = e.sm;
+            return;
+        }
+    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(4) * P.n_out, static_cast<cuuint64_t>(a.n / 4)};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(16) * P.n_out};
+    const cuuint32_t estride[2] = {1, 1};
+    for (int i = 0; i < P.n_maps; ++i) {
+        const cuuint32_t box[2] = {static_cast<cuuint32_t>(P.map_w[i]), 8};
+        if (encode(&sm.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.out, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            std::memset(&sm, 0, sizeof(sm));
+            return;
+        }
+    }
+    sm.rows4 = a.n / 4 * 4;
+    Entry& e = cache[next];
+    next = (next + 1) % 8;
+    e.out = a.out; e.n = a.n; e.n_out = P.n_out; e.n_maps = P.n_maps;
+    std::memcpy(e.w, P.map_w, sizeof(e.w));
+    e.sm = sm;
+}
+
 template <int FMT, int CG>
 inline cudaError_t launch_om(const Plan& P, const NormConsts& nc, const LaunchArgs& a, const uint8_t* w, const float* bias, int grid,
                              cudaStream_t st) {
-    if (a.out_mode == OUT_CHI2) return launch_one<FMT, CG, OM_CHI2>(P, nc, a, w, bias, grid, st);
-    if (a.out_mode == OUT_ERROR) return launch_one<FMT, CG, OM_ERROR>(P, nc, a, w, bias, grid, st);
-    return launch_one<FMT, CG, OM_ROWS>(P, nc, a, w, bias, grid, st);
+    StoreMaps smaps;
+    make_store_maps(P, a, smaps);
+    if (a.out_mode == OUT_CHI2) return launch_one<FMT, CG, OM_CHI2>(P, nc, a, w, bias, grid, st, smaps);
+    if (a.out_mode == OUT_ERROR) return launch_one<FMT, CG, OM_ERROR>(P, nc, a, w, bias, grid, st, smaps);
+    return launch_one<FMT, CG, OM_ROWS>(P, nc, a, w, bias, grid, st, smaps);
 }
 
 // cta_group: 1 = one CTA per 128-row tile, 2 = CTA pairs on 256-row super-tiles
@@ -1547,12 +1752,14 @@ inline cudaError_t launch(const Plan& P, const NormConsts& nc, const LaunchArgs&
         const long long nunits = (a.n + 2 * MT - 1) / (2 * MT);
         const int grid = 2 * static_cast<int>(std::min<long long>(nunits, sm_count / 2));
         if (a.out_mode == OUT_CHI2 || a.out_mode == OUT_ERROR || fmt == 1) return cudaErrorNotSupported;
-        return fmt == 0 ? launch_one<0, 2, OM_ROWS>(P, nc, a, static_cast<const uint8_t*>(wimg), bias, grid, st)
-                        : launch_one<2, 2, OM_ROWS>(P, nc, a, static_cast<const uint8_t*>(wimg), bias, grid, st);
+        StoreMaps smaps;
+        make_store_maps(P, a, smaps);
+        return fmt == 0 ? launch_one<0, 2, OM_ROWS>(P, nc, a, static_cast<const uint8_t*>(wimg), bias, grid, st, smaps)
+                        : launch_one<2, 2, OM_ROWS>(P, nc, a, static_cast<const uint8_t*>(wimg), bias, grid, st, smaps);
     }
 #else
     static const int cg_env = std::getenv("VAE21_TC_CTA_GROUP") ? std::atoi(std::getenv("VAE21_TC_CTA_GROUP")) : 0;
-    const int cg = (cg_env == 1 || cg_env == 2) ? cg_env : P.default_cg;
+    const int cg = (cg_env == 1 && P.nslots >= 2) ? 1 : P.default_cg;  // the one-CTA variant is an experiment switch and may not fit
     const uint8_t* w = static_cast<const uint8_t*>(wimg);
     if (cg == 2) {
         const long long nunits = (a.n + 2 * MT - 1) / (2 * MT);

@@ -50,6 +50,8 @@ for w in range(2):
     rest = m[0] - m[1:5].sum()
     print(f"  {'everything else (decode, loop, fences)':48s} {rest:12.0f}  {100 * rest / m[0]:5.1f}%   {rest / ntile:8.0f} cycles/tile")
 
+print(f" prologue warp (leader CTAs; accumulated over the 3 launches): operand computation {a[:, 5].mean() / ntile / 3:8.0f} cycles/tile, "
+      f"wait for a0 release {a[:, 6].mean() / ntile / 3:8.0f} cycles/tile")
 if hasattr(lib, "vae21_debug_tc_rec_timing") and lib.vae21_debug_tc_rec_timing(rbuf, 0) == 0:
     r = np.array(rbuf[:], dtype=np.float64).reshape(3, 256)
     n = int((r[2] > 0).sum())
