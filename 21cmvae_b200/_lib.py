@@ -26,7 +26,7 @@ PRECISIONS = {"fp32": FP32_SIMT, "fp32_simt": FP32_SIMT, "tc": TC_BF16X3, "bf16x
 
 EXPORTS = [
     "vae21_version", "vae21_last_error", "vae21_device_count", "vae21_create", "vae21_destroy",
-    "vae21_set_model", "vae21_set_norm", "vae21_predict", "vae21_forward_normalised", "vae21_chi2", "vae21_chi2_grid", "vae21_error",
+    "vae21_set_model", "vae21_set_norm", "vae21_predict", "vae21_forward_normalised", "vae21_chi2", "vae21_chi2_grid", "vae21_error", "vae21_mcmc_run",
     "vae21_host_alloc", "vae21_host_free", "vae21_host_trim", "vae21_get_info", "vae21_get_tc_stats", "vae21_time_predict",
     "vae21_trainer_create", "vae21_trainer_destroy", "vae21_trainer_num_params", "vae21_trainer_set_params",
     "vae21_trainer_get_params", "vae21_trainer_forward_backward", "vae21_trainer_adam", "vae21_trainer_epoch", "vae21_trainer_launches",
@@ -77,6 +77,8 @@ def load() -> C.CDLL:
         lib.vae21_host_trim.restype = None
         lib.vae21_get_info.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_float), C.POINTER(i32)]
         lib.vae21_get_tc_stats.argtypes = [vp, C.POINTER(i64), i32]
+        lib.vae21_mcmc_run.argtypes = [vp, vp, vp, i64, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_float),
+                                       C.POINTER(C.c_float), C.c_double, C.c_uint64, i64, i32, i32, i32, vp, C.POINTER(i64)]
         lib.vae21_time_predict.argtypes = [vp, vp, i32, i64, vp, i32, i32, C.POINTER(C.c_float)]
         lib.vae21_trainer_create.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(i32), i32, C.POINTER(vp)]
         lib.vae21_trainer_destroy.argtypes = [vp]
@@ -352,6 +354,34 @@ class Handle:
             int(first), count, obs.ctypes.data_as(C.POINTER(C.c_float)), isg.ctypes.data_as(C.POINTER(C.c_float)), optr, C.byref(bv),
             C.byref(bi), int(precision), C.c_void_p(int(stream)) if stream else None))
         return bv.value, bi.value
+
+    def mcmc_run(self, x_dev, logp_dev, lo, hi, obs, inv_sigma, a=2.0, seed=0, first_step=0, n_steps=1, init_logp=False,
+                 precision=FP32_SIMT, stream=None, want_accepted=True):
+        """n_steps stretch-move steps of the ensemble held in `x_dev` (float64 DEVICE, (walkers, n_par), coordinates of the
+        prior box) / `logp_dev` (float64 DEVICE, (walkers,)), in place.  Returns the number of accepted proposals (None when
+        `want_accepted` is false: the call then does not synchronise)."""
+        if self.dims is None:
+            raise Vae21Error(2, "model not set")
+        nd, nout = self.dims[0], self.dims[-1]
+        xptr, xdev, xshape, xdt, _, k1 = _unwrap(x_dev, want_write=True)
+        lptr, ldev, lshape, ldt, _, k2 = _unwrap(logp_dev, want_write=True)
+        if not (xdev and ldev) or np.dtype(xdt) != np.float64 or np.dtype(ldt) != np.float64:
+            raise ValueError("x_dev / logp_dev must be float64 device arrays")
+        if len(xshape) != 2 or xshape[1] != nd or tuple(lshape) != (xshape[0],):
+            raise ValueError(f"x_dev must have shape (walkers, {nd}) and logp_dev (walkers,)")
+        lo = np.ascontiguousarray(np.broadcast_to(np.asarray(lo, np.float64), (nd,)), dtype=np.float64)
+        hi = np.ascontiguousarray(np.broadcast_to(np.asarray(hi, np.float64), (nd,)), dtype=np.float64)
+        obs = np.ascontiguousarray(obs, dtype=np.float32)
+        isg = np.ascontiguousarray(np.broadcast_to(np.asarray(inv_sigma, dtype=np.float32), (nout,)))
+        if obs.shape != (nout,):
+            raise ValueError(f"obs must have shape ({nout},)")
+        acc = C.c_int64(-1)
+        _check(self._lib.vae21_mcmc_run(
+            self._h, xptr, lptr, int(xshape[0]), nd, lo.ctypes.data_as(C.POINTER(C.c_double)), hi.ctypes.data_as(C.POINTER(C.c_double)),
+            obs.ctypes.data_as(C.POINTER(C.c_float)), isg.ctypes.data_as(C.POINTER(C.c_float)), float(a), int(seed) & (2**64 - 1),
+            int(first_step), int(n_steps), 1 if init_logp else 0, int(precision), C.c_void_p(int(stream)) if stream else None,
+            C.byref(acc) if want_accepted else None))
+        return acc.value if want_accepted else None
 
     def time_predict(self, params_dev, out_dev, precision=FP32_SIMT, iters=10) -> float:
         ptr, dev, n, dt, keep = self._prep_in(params_dev, self.dims[0])

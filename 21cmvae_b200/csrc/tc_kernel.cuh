@@ -961,6 +961,11 @@ __device__ __forceinline__ void prologue_row_fixed(const LaunchArgs& a, const No
 #pragma unroll
     for (int j = 0; j < 16; ++j) x[j] = 0.f;
     if (grow >= a.n) return;
+    if (a.in_mode == IN_NORMALISED_F32) {
+#pragma unroll
+        for (int j = 0; j < K0; ++j) x[j] = reinterpret_cast<const float*>(a.in)[grow * K0 + j];
+        return;
+    }
     const bool f32_in = (a.in_mode == IN_PARAMS_F32);
     double pv[K0];
     if (f32_in) {
@@ -1340,7 +1345,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
 #pragma unroll
                 for (int rr = 0; rr < MT / 32; ++rr) {
                     float x[16];
-                    if (K0 == 7 && (a.in_mode == IN_PARAMS_F64 || a.in_mode == IN_PARAMS_F32)) prologue_row_fixed<7>(a, nc, tile * MT + rr * 32 + lane, x);
+                    if (K0 == 7 && a.in_mode != IN_GRID) prologue_row_fixed<7>(a, nc, tile * MT + rr * 32 + lane, x);
                     else prologue_row(a, nc, tile * MT + rr * 32 + lane, K0, x);
                     uint32_t w[16];
                     split16<FMT>(x, w);
@@ -1574,6 +1579,13 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                         }
                     }
                 }
+                if (OM == OM_ROWS && out_dst == DST_FINAL) {
+                    // the accumulator buffer is free as soon as it has been read: release it BEFORE the store hand-off below, which is
+                    // then off the MMA issuers' critical path
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0 && c_qbuf >= 0) signal_mma(bar_q_empty(c_qbuf));
+                }
                 if (OM == OM_ROWS && out_dst == DST_FINAL && tma_launch && !(DBG & (2 | 8))) {
                     fence_async_smem();  // the staged words are read by the async proxy
                     // earlier chunks' boxes have been read: behind the barrier everybody may overwrite the OTHER staging buffer
@@ -1599,7 +1611,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                 tc_fence_before();
                 __syncwarp();  // every lane's writes / reads are done and fenced before the elected lane signals
                 if (lane == 0) {
-                    if (c_qbuf >= 0) signal_mma(bar_q_empty(c_qbuf));
+                    if (c_qbuf >= 0 && !(OM == OM_ROWS && out_dst == DST_FINAL)) signal_mma(bar_q_empty(c_qbuf));
                     if (out_dst != DST_FINAL) signal_mma(bar_act_ready(c_idx));
                 }
             }

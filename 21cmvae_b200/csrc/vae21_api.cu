@@ -136,6 +136,8 @@ struct vae21_handle {
     // `ev_use` the last kernel launched on a caller's stream (it reads d_mu / d_obs / d_isig / the weight images)
     cudaEvent_t ev_in = nullptr, ev_use = nullptr;
     bool use_pending = false;
+    void* d_mcmc = nullptr;  // scratch of vae21_mcmc_run (proposals, stretch terms, chi^2)
+    size_t mcmc_cap = 0;
     unsigned long long* d_sat = nullptr;  // [2] saturation counters of the tensor-core operand conversion (see vae21_get_info)
     long long launches = 0;
     float last_ms = -1.f;
@@ -457,7 +459,7 @@ int vae21_destroy(vae21_handle* h) {
         cudaEventSynchronize(h->ev_use);
         cudaEventDestroy(h->ev_use);
     }
-    void* ptrs[] = {h->d_w32, h->d_b32, h->d_wtc[0], h->d_wtc[1], h->d_wtc[2], h->d_btc, h->d_mu, h->d_obs, h->d_isig, h->d_mask, h->d_key, h->d_sat};
+    void* ptrs[] = {h->d_w32, h->d_b32, h->d_wtc[0], h->d_wtc[1], h->d_wtc[2], h->d_btc, h->d_mu, h->d_obs, h->d_isig, h->d_mask, h->d_key, h->d_sat, h->d_mcmc};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete h;
@@ -762,4 +764,5 @@ int vae21_debug_tc_rec_timing(unsigned long long* out, int reset) { return tck::
 
 }  // extern "C"
 
+#include "mcmc_api.cuh"
 #include "train_api.cuh"

@@ -350,9 +350,70 @@ def main():
         e2e_s = max(e2e_ranks)
     e2e_val = world * n / e2e_s
 
+    # ---- e2e from PAGEABLE memory: what a caller of the reference API has (plain numpy in, a fresh array out)
+    pg_s = None
+    if e2e_steps > 0:
+        res_pg = emu.predict(params, precision=prec_name)
+        if world > 1:
+            dist.barrier()
+        w0 = time.perf_counter()
+        for _ in range(2):
+            res_pg = None  # a loop that drops the previous result, like an MCMC step: its block returns to the library's pinned pool
+            res_pg = emu.predict(params, precision=prec_name)
+        pg_s = (time.perf_counter() - w0) / 2
+        res_pg = None
+        if world > 1:
+            t = torch.tensor([pg_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pg_s = float(t.item())
+    # ---- the copies alone (pinned buffers, nothing else): the platform ceiling of the e2e figure on this box
+    t_in, t_out = torch.from_numpy(hp), torch.from_numpy(host_out)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    w0 = time.perf_counter()
+    for _ in range(2):  # both directions at once (cudaMemcpyAsync on two streams; the buffers are cudaHostAlloc'ed by the library)
+        with torch.cuda.stream(s_in):
+            d_params.copy_(t_in, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            t_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+    copy_s = (time.perf_counter() - w0) / 2
+    if world > 1:
+        t = torch.tensor([copy_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        copy_s = float(t.item())
+    # ---- the north star's NAMED tensor-core format as well, when the headline runs another one
+    also = None
+    if tc and prec_name != "bf16x3" and prec_name != "fp32":
+        p2 = L.PRECISIONS["bf16x3"]
+        for _ in range(3):
+            h.predict(d_params, out=d_out, precision=p2, stream=stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        k2 = max(10, min(args.steps, 30))
+        e0.record(stream)
+        for _ in range(k2):
+            h.predict(d_params, out=d_out, precision=p2, stream=stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1) / k2
+        if world > 1:
+            t = torch.tensor([ms2], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms2 = float(t.item())
+        also = {"precision_path": "bf16x3", "ms_per_step": ms2, "value": world * n / (ms2 * 1e-3), "steps": k2}
+
     if rank == 0:
         pk = peaks()
         per_gpu_rate = n / (ms_step * 1e-3)
+        if also:
+            r2 = n / (also["ms_per_step"] * 1e-3)
+            also["frac_executed"] = r2 * 2 * TC_PASSES["bf16x3"] * PADDED_MAC_PER_SIGNAL / 1e12 / pk["bf16_tflops"]
+            also["frac_algorithmic"] = r2 * FLOP_PER_SIGNAL / 1e12 / pk["bf16_tflops"]
+            also["passes"] = TC_PASSES["bf16x3"]
         if prec_name == "fp32":
             # CUDA-core path: neither named roof binds; report against the HBM roof (the other candidate)
             ach = per_gpu_rate * BYTES_PER_SIGNAL_F64 / 1e9
@@ -371,9 +432,16 @@ def main():
                     "hbm_gbs_achieved": per_gpu_rate * BYTES_PER_SIGNAL_F64 / 1e9,
                     "note": "achieved = algorithmic 740,608 FLOP/signal; frac_executed counts the tensor-pipe passes per k-step "
                             "(in kind::f16-MMA units, see `passes`) and the MMA-shape padding actually issued"}
+        # DRAM bytes per launch of this kernel from the committed ncu capture (cannot be measured inside an unprofiled run): the
+        # source names the capture, so a stale number is visible as such
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tp):
-            roof["traffic"] = json.load(open(tp)).get(prec_name)
+            tj = json.load(open(tp))
+            ent = tj.get(prec_name)
+            if isinstance(ent, dict):
+                roof["traffic"], roof["traffic_source"] = ent.get("bytes"), ent.get("source")
+            elif ent is not None:
+                roof["traffic"], roof["traffic_source"] = ent, tj.get("source", "profiles/traffic.json")
         cpu = None
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is a rank-0, N = 1 measurement
             threads = len(os.sched_getaffinity(0))
@@ -391,10 +459,15 @@ def main():
             "data": "synthetic",
             "config": {"workload": "DirectEmulator.predict 7->288->352->288->224->451, full 451-bin output to HBM",
                        "rows_per_gpu": n, "params_dtype": "f64", "precision_path": prec_name,
-                       "weights": "random-init (Glorot), shipped emulator.h5 absent from the reference checkout",
+                       "weights": build_problem.weights,
                        "l2": "working set 1.86 GB/step >> 126 MB L2 (no flush needed)", "parallelism": f"rows sharded x{world}", "host_cores_bound": (len(numa_cores) if numa_cores else None)},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * 56, "d2h_bytes_per_step": n * 1804,
-                    "steps": e2e_steps, "checksum": checksum, "seconds_per_step_by_rank": e2e_ranks},
+                    "steps": e2e_steps, "checksum": checksum, "seconds_per_step_by_rank": e2e_ranks,
+                    "platform_ceiling": world * n / copy_s, "platform_ceiling_gbs": world * n * 1860 / copy_s / 1e9,
+                    "platform_ceiling_note": "the same bytes moved by cudaMemcpyAsync alone between the same pinned buffers, no kernel"},
+            "e2e_pageable": ({"value": world * n / pg_s, "unit": UNIT,
+                              "note": "plain numpy in, a fresh array out (the reference API's calling convention)"} if pg_s else None),
+            "also": also,
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "check": {"max_abs_err_mK": max_mk, "max_err_over_amplitude": rel, "rows_checked": int(len(idx))},
         }

@@ -128,6 +128,22 @@ int vae21_chi2_grid(vae21_handle* h, int n_dim, const int* npts, const double* x
                     void* stream);
 
 /*
+ * Ensemble MCMC (BASELINE config 4; the reference has no sampler -- its users put DirectEmulator.predict, emulator.py:383-407, inside
+ * their own likelihood): n_steps stretch-move steps (Goodman & Weare 2010, scale a, red/blue halves) of an ensemble of n_walkers
+ * (even) walkers with ln p = -chi^2 / 2 inside the box [lo, hi] and -inf outside, entirely on the device: per half-step one
+ * proposal kernel, one fused emulate + chi^2 launch on the proposals, one accept kernel.
+ *   x_dev [n_walkers, n_dim] float64 DEVICE: positions in the coordinates of preprocess.par_transform's box (log10 on the masked
+ *     columns), updated in place;  logp_dev [n_walkers] float64 DEVICE: ln p of the positions, updated in place (computed first when
+ *     init_logp != 0);  lo / hi: host, same coordinates;  obs / inv_sigma: host, as in vae21_chi2.
+ *   Random numbers are a stateless hash of (seed, first_step + s, half, walker, draw): a run can be continued by passing the next
+ *   first_step, and oracle/mcmc_ref.py restates the generator.  n_accepted (host, may be NULL: then the call does not synchronise)
+ *   receives the number of accepted proposals of this call.
+ */
+int vae21_mcmc_run(vae21_handle* h, double* x_dev, double* logp_dev, int64_t n_walkers, int n_dim, const double* lo, const double* hi,
+                   const float* obs, const float* inv_sigma, double a, uint64_t seed, int64_t first_step, int n_steps, int init_logp,
+                   int precision, void* stream, int64_t* n_accepted);
+
+/*
  * Fused figure of merit (emulator.py:129-192 `error`, :409-439 `test_error`): err[i] = sqrt(mean_k (predict(params_i)[k] -
  * truth[i][k])^2) over the bins with band_mask[k] != 0 (NULL = all bins), in mK; with relative != 0 divided by max_k |truth[i][k]|
  * over the same bins and multiplied by 100 (%).  The 451-bin predictions never leave the GPU.  params / truth / err may each be
