@@ -1,0 +1,138 @@
+"""GPU, world size 2 over NCCL (skipped on boxes with one GPU): the collectives BASELINE configs 3 and 5 use -- the global chi^2
+argmin of a sharded parameter batch, and the gradient all-reduce of data-parallel retraining (reference emulator.py:339-381)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from conftest import GOLDEN, ROOT, pkg
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _need_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on one node")
+
+
+def _spawn(worker, world=2, timeout=300):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=timeout) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return res
+
+
+def _init(rank, world, port):
+    import sys
+
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    return dist
+
+
+def _trained_emulator(device):
+    import importlib
+
+    emu = importlib.import_module("21cmvae_b200.emulator")
+    pp = importlib.import_module("21cmvae_b200.preprocess")
+    d = np.load(os.path.join(GOLDEN, "direct_trained.npz"))
+    e = emu.DirectEmulator(stats=pp.NormStats(d["par_min"], d["par_max"], d["sig_mean"], np.float32(d["sig_std"])), device=device)
+    e.load_model(os.path.join(GOLDEN, "direct_trained.h5"))
+    return e, d
+
+
+def _argmin_worker(rank, world, port, q):
+    dist = _init(rank, world, port)
+    try:
+        import importlib
+
+        mg = importlib.import_module("21cmvae_b200.multigpu")
+        from oracle import refmath as rm
+
+        e, d = _trained_emulator(rank)
+        params = rm.draw_params(20_001, seed=77)
+        params[15_432] = d["par_test"][5]
+        obs = e.predict(d["par_test"][5], precision="fp32")
+        out = {}
+        for prec in ("fp32", "fp16e4m3"):
+            sh = mg.ShardedEmulator(e, rank, world)
+            out[prec] = sh.chi2_argmin(params, obs, np.full(451, 3.0), precision=prec)
+        single = e.chi2(params, obs, np.full(451, 3.0), precision="fp32", return_argmin=True)[1:] if rank == 0 else None
+        sums = mg.allreduce_sums(np.array([1.0, float(rank)]))
+        q.put((rank, (out, single, sums.tolist())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_global_argmin_of_a_sharded_batch():
+    _need_two_gpus()
+    res = _spawn(_argmin_worker)
+    (o0, single, s0), (o1, _, s1) = res[0], res[1]
+    assert s0 == s1 == [2.0, 1.0]
+    for prec in ("fp32", "fp16e4m3"):
+        assert o0[prec] == o1[prec]                      # every rank holds the same global answer
+        assert o0[prec][1] == 15_432                     # the planted row, in GLOBAL numbering (it lives on rank 1)
+    assert o0["fp32"][0] == pytest.approx(single[0], rel=1e-6, abs=1e-6) and single[1] == 15_432
+    assert o0["fp32"][0] < 1e-3
+
+
+def _dp_worker(rank, world, port, q):
+    dist = _init(rank, world, port)
+    try:
+        import importlib
+
+        tr = importlib.import_module("21cmvae_b200.training")
+        from oracle import refmath as rm
+
+        dims = (7, 288, 352, 288, 224, 451)
+        ks, bs, relu = rm.glorot_chain(dims, seed=5)
+        rng = np.random.default_rng(6)
+        n = 700  # two full batches of 256 and a short one
+        x = rng.uniform(-1, 1, size=(n, 7)).astype(np.float32)
+        y = rng.normal(size=(n, 451)).astype(np.float32)
+        w = (1.0 / rng.uniform(0.5, 2.0, size=n) ** 2).astype(np.float32)
+        flat = tr.flatten_weights(ks, bs)
+        out, hist = tr.fit(dims, [int(r) for r in relu], flat, x, y, w, optimizer=tr.Adam(1e-3), epochs=2, batch_size=256, seed=9,
+                           device=rank, distributed=True)
+        ref = None
+        if rank == 0:
+            ref, hist1 = tr.fit(dims, [int(r) for r in relu], flat, x, y, w, optimizer=tr.Adam(1e-3), epochs=2, batch_size=256, seed=9,
+                                device=0, distributed=False)
+            ref = (ref, hist1["loss"])
+        q.put((rank, (out, hist["loss"], ref)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_data_parallel_training_equals_single_gpu():
+    _need_two_gpus()
+    res = _spawn(_dp_worker)
+    (p0, l0, ref), (p1, l1, _) = res[0], res[1]
+    assert np.array_equal(p0, p1)  # replicas stay bit-identical: same all-reduced gradient, same Adam
+    ref_p, ref_l = ref
+    scale = np.abs(ref_p).max()
+    assert np.max(np.abs(p0 - ref_p)) <= 2e-4 * scale  # sharded batch sums differ from the full-batch sum only in rounding
+    assert np.allclose(l0, ref_l, rtol=1e-4) and np.allclose(l0, l1, rtol=1e-6)
