@@ -62,6 +62,9 @@ constexpr int NFULL = 4;          // ring of "accumulator chunk ready" barriers
                            // 16 no hi/lo split arithmetic, 32 no hidden-layer operand writes, 128 no weight ring at all (MMAs read stale smem)
 #endif
 constexpr int DBG = VAE21_TC_ABLATE;
+#ifndef VAE21_TC_EPI_SINGLE
+#define VAE21_TC_EPI_SINGLE 0  // 1: a single instantiation of the epilogue's group body (smaller code, 16 extra moves per group)
+#endif
 #ifndef VAE21_TC_STORE_DBG
 #define VAE21_TC_STORE_DBG 0  // profiling only (bit mask): 1 no box store issue, 2 no scalar stores around the boxes, 4 no wait for earlier boxes, 8 no barrier
 #endif
@@ -350,7 +353,8 @@ inline bool build_plan_with(bool first_to_tmem, int n_layers, const int* dims, c
         const int units = L.Npad / 16;
         int maxcols, q0 = 0, qsize = 0, nbuf = 2;
         if (L.out_dst == DST_TMEM) {
-            maxcols = 224;  // stage = ncols * 16 k * 2 B * (hi + lo) <= 14336 B
+            static const int inplace_max = std::getenv("VAE21_TC_INPLACE_MAX") ? std::atoi(std::getenv("VAE21_TC_INPLACE_MAX")) : 224;
+            maxcols = std::max(16, std::min(224, inplace_max / 16 * 16));  // stage = ncols * 16 k * 2 B * (hi + lo) <= 14336 B
             if (L.Npad > 512) { why = "in-place layer too wide"; return false; }
         } else {
             // layer 0 shares the ring geometry of the last layer (their accumulators overlap in
@@ -1427,7 +1431,8 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
         const int shift = (4 - ((q_res * NO) & 3)) & 3;
         const bool tma_launch = (OM == OM_ROWS) && smaps.rows4 > 0;
         uint8_t* const stage_base = sm + P.off_stage + (sub * 4 + q_res) * P.stage_sq;
-        const bool issuer = (half == 0 && lane < 4);                  // lane q issues the box of residue q
+        const bool issuer = (half == 0 && lane < 4);                  // lane q of the first column share issues the box of residue q
+                                                                      // (one lane of each of the four shares: measured 2 % slower)
 
         // hand-off to the MMA issuers, which live in the leader CTA of a pair
         auto signal_mma = [&](uint32_t bar) {
@@ -1565,6 +1570,22 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                     }
                 };
                 if (g_lo < g_hi && !(DBG & 2)) {
+#if VAE21_TC_EPI_SINGLE
+                    // one instantiation of the group body (half the epilogue's code): the prefetched registers are moved, not renamed
+                    uint32_t ra[16], rb[16];
+                    tmem_ld16(tbase + static_cast<uint32_t>(16 * g_lo), ra);
+#pragma unroll 1
+                    for (int g = g_lo; g < g_hi; ++g) {
+                        tmem_ld_wait();
+                        if (g + 1 < g_hi) tmem_ld16(tbase + static_cast<uint32_t>(16 * (g + 1)), rb);
+                        process(ra, g);
+                        if (g + 1 < g_hi) {
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) ra[i] = rb[i];
+                        }
+                    }
+#else
                     uint32_t ra[16], rb[16];
                     tmem_ld16(tbase + static_cast<uint32_t>(16 * g_lo), ra);
 #pragma unroll 1
@@ -1578,6 +1599,7 @@ vae21_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ NormCons
                             process(rb, g + 1);
                         }
                     }
+#endif
                 }
                 if (OM == OM_ROWS && out_dst == DST_FINAL) {
                     // the accumulator buffer is free as soon as it has been read: release it BEFORE the store hand-off below, which is

@@ -139,8 +139,13 @@ def load_dense_chain(path: str) -> DenseChainWeights:
             biases.append(np.ascontiguousarray(b, dtype=np.float32))
             names.append(ln)
             relu.append(acts.get(ln, None))
-        # without a model_config (weights-only file) assume relu on all but the last layer
+        # A weights-only file (no model_config) carries no activations: assume relu on all but the last layer, the architecture of
+        # every model the reference ships.  A file WITH a model_config whose layer names do not cover the weight layers is
+        # inconsistent -- refuse it instead of silently replacing every activation.
         if any(r is None for r in relu):
+            if acts:
+                missing = [n for n, r in zip(names, relu) if r is None]
+                raise IOError(f"{path}: model_config has no entry for weight layer(s) {missing}")
             relu = [True] * (len(kernels) - 1) + [False]
         out = DenseChainWeights(kernels, biases, [bool(r) for r in relu], names, model_name,
                                 _as_str(attrs["keras_version"]) if "keras_version" in attrs else "")

@@ -11,7 +11,7 @@ if _root not in _sys.path:
     _sys.path.insert(0, _root)
 _pkg = _il.import_module("21cmvae_b200")
 __version__ = _pkg.__version__
-for _name in ("preprocess", "emulator", "keras_h5", "multigpu", "training"):
+for _name in ("preprocess", "emulator", "keras_h5", "multigpu", "training", "mcmc"):
     _mod = _il.import_module("21cmvae_b200." + _name)
     _sys.modules[__name__ + "." + _name] = _mod
     globals()[_name] = _mod

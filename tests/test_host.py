@@ -76,6 +76,30 @@ def test_invalid_model_path_raises_ioerror(tmp_path):
         kh.load_dense_chain(str(bad))
 
 
+def test_model_config_that_does_not_cover_the_weight_layers_is_refused(tmp_path):
+    """A file whose model_config names other layers than model_weights must not load with guessed activations."""
+    import json
+
+    kh = pkg("keras_h5")
+    h5 = pkg("h5lite")
+    cfg = {"class_name": "Sequential", "config": {"name": "m", "layers": [
+        {"class_name": "Dense", "config": {"name": "other_0", "units": 3, "activation": "relu"}},
+        {"class_name": "Dense", "config": {"name": "other_1", "units": 2, "activation": "linear"}}]}}
+    wr = h5.Writer()
+    wr.set_attr("/", "keras_version", "2.7.0")
+    wr.set_attr("/", "model_config", json.dumps(cfg))
+    wr.create_group("/model_weights")
+    wr.set_attr("/model_weights", "layer_names", ["dense_0", "dense_1"])
+    for n, (i, o) in zip(("dense_0", "dense_1"), ((4, 3), (3, 2))):
+        wr.create_dataset(f"/model_weights/{n}/{n}/kernel:0", np.zeros((i, o), np.float32))
+        wr.create_dataset(f"/model_weights/{n}/{n}/bias:0", np.zeros((o,), np.float32))
+        wr.set_attr(f"/model_weights/{n}", "weight_names", [f"{n}/kernel:0", f"{n}/bias:0"])
+    p = str(tmp_path / "inconsistent.h5")
+    wr.save(p)
+    with pytest.raises(IOError):
+        kh.load_dense_chain(p)
+
+
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present")
 def test_reads_the_shipped_reference_models(ae_golden):
     kh = pkg("keras_h5")
