@@ -1,25 +1,24 @@
 // tcgen05 / TMEM tensor-core path of the fused emulator kernel (sm_100a).
 //
-// One persistent CTA per SM processes 128-row tiles.  All Dense layers of a tile are chained
-// on-chip: every layer is a sequence of tcgen05.mma (kind::f16, M=128, fp32 accumulate in TMEM)
-// in a 3-pass split  D += A_hi*W_hi + A_hi*W_lo + A_lo*W_hi  (bf16 or fp16 hi/lo pairs), the
-// epilogue warps read the accumulators back with tcgen05.ld, add bias, apply ReLU, split the
-// result into hi/lo again and hand it to the next layer either through shared memory (UMMA
-// "SS" operand) or -- converted IN PLACE over the accumulator columns -- through TMEM (UMMA
-// "TS" operand).  Weights (1.5 MB of packed hi/lo operand images, L2 resident) stream through a
-// ring of shared-memory stages filled by 1-D bulk (TMA) copies.  The first layer's operand
-// comes from the fused parameter transform, the last layer's epilogue applies the output
-// transform (or the chi^2 reduction) and writes coalesced row segments.
+// One persistent CTA per SM (a cluster of two works on a 256-row super-tile with cta_group::2 MMAs) processes 128-row tiles.  All
+// Dense layers of a tile are chained on-chip: every layer is a sequence of tcgen05.mma (M = 128 per CTA, fp32 accumulate in TMEM)
+// in a split product  D += A_hi*W_hi + A_hi*W_lo + A_lo*W_hi  -- three kind::f16 passes (bf16 or fp16 hi/lo pairs), or one
+// kind::f16 pass plus one kind::f8f6f4 pass carrying both corrections --, the epilogue warps read the accumulators back with
+// tcgen05.ld, add bias, apply ReLU, split the result again and hand it to the next layer either through shared memory (UMMA "SS"
+// operand) or -- converted IN PLACE over the accumulator columns -- through TMEM (UMMA "TS" operand).  Weights (1.5 MB of packed
+// operand images, L2 resident) stream through a ring of shared-memory slots filled by 1-D bulk (TMA) copies.  The first layer's
+// operand comes from the fused parameter transform; the last layer's epilogue applies the output transform (or the chi^2
+// reduction) and writes the spectra through tensor-map (TMA) box stores.
 //
-// Warp roles (128 + 128 EPS threads): role 0 = bulk-copy producer, role 1 = MMA issuer (also allocates TMEM; in the follower CTA of a
-// pair it forwards "my half of this ring slot has landed" to the leader), roles 2 and 3 = prologue (parameter transform ->
-// layer-0 operand, one tile ahead, 64 rows each), roles 4.. = epilogue (thread = tile row = TMEM lane).
+// Warp roles (128 + 128 EPS threads): role 0 = bulk-copy producer; roles 1 and 3 = MMA issuers, interpreting the host-built issue
+// table (build_iters) record by record under a baton that fixes the issue order (role 1 also allocates TMEM; in the follower CTA of
+// a pair it forwards "my half of this ring slot has landed" to the leader); role 2 = prologue (parameter transform -> layer-0
+// operand, one tile ahead); roles 4.. = epilogue (thread = tile row = TMEM lane).
 //
-// Code size is a first-class constraint of this kernel: the four roles execute disjoint code, and when the whole kernel does not
-// fit the SM's instruction cache the lone MMA-issuing warp -- whose loop is re-fetched after every pass of the sixteen epilogue warps
-// through theirs -- stalls on instruction fetch for most of its time (round 2 measurement, profiles/README.md: 8.5 % of instruction
-// cache requests missed in the 135 KB round-1 kernel, and every instruction ADDED to the issue loop cost ~100 cycles).  Hence: the
-// output mode is a template parameter, every hot loop exists exactly once (no hand-unrolled copies), rare paths are __noinline__.
+// History of the control path (profiles/README.md): the round-1 kernel walked layers and chunks in the issuing warp; measured in
+// round 2, that lone warp was busy EXECUTING control instructions (chunk set-up, dependent constant loads, barrier bookkeeping) for
+// 76 % of the launch.  The schedule is therefore flattened on the host into one 16-byte record per ring slot, and the output mode is a
+// template parameter (each instantiation carries only its own final-layer code).
 //
 // Operand images (validated on hardware by tools/umma_probe.cu):
 //   un-swizzled K-major core-matrix layout [k/8][row][8 x 16-bit]: descriptor LBO = bytes between
