@@ -26,7 +26,7 @@ PRECISIONS = {"fp32": FP32_SIMT, "fp32_simt": FP32_SIMT, "tc": TC_BF16X3, "bf16x
 
 EXPORTS = [
     "vae21_version", "vae21_last_error", "vae21_device_count", "vae21_create", "vae21_destroy",
-    "vae21_set_model", "vae21_set_norm", "vae21_predict", "vae21_forward_normalised", "vae21_chi2", "vae21_chi2_grid", "vae21_error", "vae21_mcmc_run",
+    "vae21_set_model", "vae21_set_norm", "vae21_predict", "vae21_forward_normalised", "vae21_chi2", "vae21_chi2_grid", "vae21_error", "vae21_mcmc_run", "vae21_check_plan",
     "vae21_host_alloc", "vae21_host_free", "vae21_host_trim", "vae21_get_info", "vae21_get_tc_stats", "vae21_time_predict",
     "vae21_trainer_create", "vae21_trainer_destroy", "vae21_trainer_num_params", "vae21_trainer_set_params",
     "vae21_trainer_get_params", "vae21_trainer_forward_backward", "vae21_trainer_adam", "vae21_trainer_epoch", "vae21_trainer_launches",
@@ -79,6 +79,7 @@ def load() -> C.CDLL:
         lib.vae21_get_tc_stats.argtypes = [vp, C.POINTER(i64), i32]
         lib.vae21_mcmc_run.argtypes = [vp, vp, vp, i64, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_float),
                                        C.POINTER(C.c_float), C.c_double, C.c_uint64, i64, i32, i32, i32, vp, C.POINTER(i64)]
+        lib.vae21_check_plan.argtypes = [i32, C.POINTER(i32), C.c_char_p, i32]
         lib.vae21_time_predict.argtypes = [vp, vp, i32, i64, vp, i32, i32, C.POINTER(C.c_float)]
         lib.vae21_trainer_create.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(i32), i32, C.POINTER(vp)]
         lib.vae21_trainer_destroy.argtypes = [vp]
@@ -98,6 +99,16 @@ def load() -> C.CDLL:
 def _check(rc: int):
     if rc != 0:
         raise Vae21Error(rc, load().vae21_last_error().decode("utf-8", "replace"))
+
+
+def check_plan(dims):
+    """Host-only self-check of the tensor-core schedule of a Dense stack: (code, reason) with code 0 = consistent schedule,
+    1 = the stack does not fit the tensor-core kernel, 2 = inconsistent schedule (a planner bug)."""
+    lib = load()
+    d = (C.c_int32 * len(dims))(*[int(v) for v in dims])
+    buf = C.create_string_buffer(256)
+    rc = lib.vae21_check_plan(len(dims) - 1, d, buf, 256)
+    return rc, buf.value.decode("utf-8", "replace")
 
 
 def device_count() -> int:

@@ -590,6 +590,150 @@ inline bool build_plan(int n_layers, const int* dims, const float* const* kernel
     return false;
 }
 
+// ---- schedule self-check (host only) ------------------------------------------------------------
+// Replays the issue table of a plan against the epilogue's arrivals for a few tiles and verifies what the device protocol relies on:
+//   * the records of every chunk cover its k-steps exactly once, in order, the first one overwriting the accumulator;
+//   * every chunk's "accumulator complete" barrier gets exactly two commits, on its last one or two records; layer 0 commits the
+//     "a0 may be overwritten" barrier once per record and the barrier is initialised with that count;
+//   * every flagged wait names the phase it means: mbarrier waits are by phase PARITY, so at the time of a wait the previous phase
+//     of that barrier must be known complete (an earlier record waited for it) and the phase after the awaited one must not be able to
+//     complete before this record is issued -- otherwise the wait passes on a stale phase or blocks for ever.
+// Run by vae21_check_plan (C ABI, no GPU needed) in the CPU tests over many layer stacks.
+inline bool check_schedule(const Plan& P, const std::vector<float>& bias_img, std::string& why) {
+    for (int v = 0; v < 2; ++v) {
+        if (v == 0 && P.nslots < 2) continue;  // the one-CTA variant is optional
+        const int n_iter = P.n_iter[v];
+        const uint32_t* tab = reinterpret_cast<const uint32_t*>(bias_img.data()) + P.iter_off[v];
+        if (P.iter_off[v] + 4 * n_iter > static_cast<int>(bias_img.size())) { why = "issue table outside the bias image"; return false; }
+        // --- per-chunk structure
+        std::vector<int> first_rec(P.n_chunks, -1), last_rec(P.n_chunks, -1);
+        int r = 0, l0 = 0;
+        for (int c = 0; c < P.n_chunks; ++c) {
+            const Chunk& C = P.C[c];
+            const int kps = v ? C.kps2 : 1;
+            int k = 0, commits = 0;
+            first_rec[c] = r;
+            while (k < C.nstages) {
+                if (r >= n_iter) { why = "issue table too short"; return false; }
+                const uint32_t w0 = tab[4 * r], w1 = tab[4 * r + 1], w2 = tab[4 * r + 2];
+                const int nk = (w2 >> 9) & 7;
+                if (static_cast<int>(w2 >> 20) != c || static_cast<int>(w2 & 0x1ff) != C.ncols || nk < 1 || nk > kps || nk > 4) { why = "record does not match its chunk"; return false; }
+                if (((w2 & IT_FIRST) != 0) != (k == 0)) { why = "accumulate flag"; return false; }
+                if (((w2 & IT_TS) != 0) != (C.a_src == A_TMEM)) { why = "operand source flag"; return false; }
+                if (static_cast<int>(w0 >> 16) != C.dcol || w1 != (static_cast<uint32_t>(C.ncols >> 3) << 17)) { why = "accumulator column / descriptor bits"; return false; }
+                const uint32_t a = w0 & 0xffffu;
+                const uint32_t want_a = (C.a_src == A_TMEM) ? 16u * k : static_cast<uint32_t>(((C.a_src == A_SMEM_A0 ? P.off_a0 : P.off_act) + k * KSTEP_BYTES) >> 4);
+                if (a != want_a) { why = "A operand cursor"; return false; }
+                const int nc = (w2 >> 14) & 3;
+                commits += nc;
+                if (nc && k + nk < C.nstages && k + nk + kps < C.nstages) { why = "accumulator commit before the last two records"; return false; }
+                if (((w2 & IT_A0FREE) != 0) != (C.layer == 0)) { why = "a0-free flag"; return false; }
+                if (C.layer == 0) ++l0;
+                k += nk;
+                ++r;
+            }
+            last_rec[c] = r - 1;
+            if (k != C.nstages || commits != 2) { why = "k-steps / commit count of a chunk"; return false; }
+        }
+        if (r != n_iter || l0 != P.l0_iters[v]) { why = "record count"; return false; }
+        // --- barrier phases over three tiles.  Producer events per barrier, in the epilogue's (= chunk) order; event e of a barrier
+        // can only have happened once the last record of its chunk has been issued.
+        const int T = 3;
+        struct Ev { long long after_rec; };  // global index of the record that must have been issued before the event can happen
+        std::vector<std::vector<Ev>> ev(64);
+        for (int t = 0; t < T; ++t) {
+            // the prologue runs one tile ahead: a0 of tile t is written once the layer-0 MMAs of tile t - 1 have released it
+            {
+                int l0_last = 0;
+                for (int c = 0; c < P.n_chunks; ++c)
+                    if (P.C[c].layer == 0) l0_last = last_rec[c];
+                ev[BAR_IDX_A0_READY].push_back({t == 0 ? -1 : static_cast<long long>(t - 1) * n_iter + l0_last});
+            }
+            for (int c = 0; c < P.n_chunks; ++c) {
+                const Chunk& C = P.C[c];
+                const long long lr = static_cast<long long>(t) * n_iter + last_rec[c];
+                if (C.qbuf >= 0) ev[BAR_IDX_Q_EMPTY + C.qbuf].push_back({lr});
+                if (C.out_dst != DST_FINAL) ev[BAR_IDX_ACT_READY + C.idx_in_layer].push_back({lr});
+            }
+        }
+        std::vector<long long> known(64, 0);  // phases of a barrier known complete to the issuers (an earlier record waited for them)
+        for (int t = 0; t < T; ++t) {
+            std::vector<int> uq(2, 0);
+            for (int c = 0; c < P.n_chunks; ++c) {
+                const Chunk& C = P.C[c];
+                for (int rr = first_rec[c]; rr <= last_rec[c]; ++rr) {
+                    const long long g = static_cast<long long>(t) * n_iter + rr;
+                    const uint32_t w3 = tab[4 * rr + 3];
+                    auto wait = [&](int bar, uint32_t parity, long long n_req) -> bool {
+                        // n_req = number of completed phases the wait is meant to see
+                        if (n_req < 1 || n_req > static_cast<long long>(ev[bar].size())) { why = "wait for a phase nobody produces"; return false; }
+                        if (parity != static_cast<uint32_t>((n_req - 1) & 1)) { why = "wait parity"; return false; }
+                        if (known[bar] < n_req - 1) { why = "wait for phase n + 1 before phase n is known complete (stale pass)"; return false; }
+                        if (ev[bar][n_req - 1].after_rec >= g) { why = "wait for an arrival that needs this record (deadlock)"; return false; }
+                        if (n_req < static_cast<long long>(ev[bar].size()) && ev[bar][n_req].after_rec < g) { why = "the next phase can complete before this wait (missed phase)"; return false; }
+                        known[bar] = std::max(known[bar], n_req);
+                        return true;
+                    };
+                    const uint32_t q = w3 & 0xffu;
+                    const uint32_t tpar = t & 1;
+                    if (q & 3u) {
+                        const int b = static_cast<int>(q & 3u) - 1;
+                        if (rr != first_rec[c] || b != C.qbuf) { why = "accumulator wait on the wrong record"; return false; }
+                        const long long use = static_cast<long long>(t) * 0;  // computed below from the event list
+                        (void)use;
+                        // this is use number u (global) of buffer b: it needs the drain of use u - 1 = event u - 1 ... i.e. u completed phases
+                        long long u = 0;
+                        for (int tt = 0; tt <= t; ++tt)
+                            for (int cc = 0; cc < P.n_chunks; ++cc)
+                                if (P.C[cc].qbuf == b && (tt < t || cc < c)) ++u;
+                        const bool skip = (q & 16u) && t == 0;
+                        if ((u == 0) != skip) { why = "first-use flag of an accumulator buffer"; return false; }
+                        if (!skip && !wait(BAR_IDX_Q_EMPTY + b, ((q >> 2) ^ ((q >> 3) & tpar)) & 1u, u)) return false;
+                    } else if (rr == first_rec[c] && C.qbuf >= 0) {
+                        why = "missing accumulator wait";
+                        return false;
+                    }
+                    for (int i = 1; i < 4; ++i) {
+                        const uint32_t e = (w3 >> (8 * i)) & 0xffu;
+                        if (!e) continue;
+                        const int bar = static_cast<int>(e & 63u);
+                        const uint32_t parity = ((e >> 6) ^ ((e >> 7) & tpar)) & 1u;
+                        long long n_req;
+                        if (bar == BAR_IDX_A0_READY) {
+                            if (!(C.layer == 0 && C.idx_in_layer == 0 && rr == first_rec[c])) { why = "a0 wait on the wrong record"; return false; }
+                            n_req = t + 1;
+                        } else if (bar >= BAR_IDX_ACT_READY && bar < BAR_IDX_ACT_READY + MAX_LCHUNK) {
+                            if (C.layer == 0 || C.idx_in_layer != 0) { why = "operand wait outside the first chunk of a layer"; return false; }
+                            const int j = bar - BAR_IDX_ACT_READY;
+                            if (j >= P.L[C.layer - 1].nchunks) { why = "operand wait for a chunk the producing layer does not have"; return false; }
+                            // the k-steps of this record must not precede the awaited chunk's columns; earlier records must not reach them
+                            n_req = known[bar] + 1;
+                            long long cnt = 0;  // events on this barrier up to and including chunk (src_first + j) of tile t
+                            for (int tt = 0; tt <= t; ++tt)
+                                for (int cc = 0; cc < P.n_chunks; ++cc)
+                                    if (P.C[cc].out_dst != DST_FINAL && P.C[cc].idx_in_layer == j && (tt < t || cc <= C.src_first + j)) ++cnt;
+                            if (cnt != n_req) { why = "operand wait does not follow the producing chunks in order"; return false; }
+                        } else {
+                            why = "unknown barrier in a wait";
+                            return false;
+                        }
+                        if (!wait(bar, parity, n_req)) return false;
+                    }
+                }
+            }
+            // every operand chunk of every layer must have been waited for by the end of the layer's first chunk: checked through
+            // `known` at the end of the tile
+            for (int j = 0; j < MAX_LCHUNK; ++j) {
+                long long cnt = 0;
+                for (int cc = 0; cc < P.n_chunks; ++cc)
+                    if (P.C[cc].out_dst != DST_FINAL && P.C[cc].idx_in_layer == j) ++cnt;
+                if (known[BAR_IDX_ACT_READY + j] != cnt * (t + 1)) { why = "an operand chunk is never waited for"; return false; }
+            }
+        }
+    }
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Device helpers
 // ---------------------------------------------------------------------------------------------

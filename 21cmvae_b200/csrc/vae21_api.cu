@@ -755,6 +755,34 @@ int vae21_time_predict(vae21_handle* h, const void* params_dev, int params_dtype
     return 0;
 }
 
+int vae21_check_plan(int n_layers, const int* dims, char* msg, int msg_len) {
+    // Host only: plan the tensor-core schedule of a Dense stack (zero weights: only shapes matter) and replay it (tck::check_schedule).
+    // 0 = the stack has a valid schedule, 1 = it does not fit the tensor-core kernel (msg says why), 2 = the schedule is inconsistent.
+    if (!dims || n_layers < 1 || n_layers > VAE21_MAX_LAYERS) return fail(VAE21_ERR_ARG, "bad layer stack");
+    std::vector<std::vector<float>> ks(n_layers), bs(n_layers);
+    std::vector<const float*> kp(n_layers), bp(n_layers);
+    std::vector<int> relu(n_layers, 1);
+    relu[n_layers - 1] = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        if (dims[l] < 1 || dims[l + 1] < 1) return fail(VAE21_ERR_ARG, "bad layer width");
+        ks[l].assign(static_cast<size_t>(dims[l]) * dims[l + 1], 0.f);
+        bs[l].assign(dims[l + 1], 0.f);
+        kp[l] = ks[l].data();
+        bp[l] = bs[l].data();
+    }
+    tck::Plan P;
+    std::vector<unsigned short> img[3];
+    std::vector<float> bias_img;
+    std::string why;
+    int rc = 0;
+    if (!tck::build_plan(n_layers, dims, kp.data(), bp.data(), relu.data(), P, img, bias_img, why)) rc = 1;
+    else if (!tck::check_schedule(P, bias_img, why)) rc = 2;
+    if (msg && msg_len > 0) {
+        std::snprintf(msg, static_cast<size_t>(msg_len), "%s", why.c_str());
+    }
+    return rc;
+}
+
 #if VAE21_TC_TIMING
 // profiling builds only (not declared in vae21.h)
 int vae21_debug_tc_timing(long long* out) { return tck::read_timing(out) == cudaSuccess ? 0 : 3; }

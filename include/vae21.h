@@ -144,6 +144,14 @@ int vae21_mcmc_run(vae21_handle* h, double* x_dev, double* logp_dev, int64_t n_w
                    int precision, void* stream, int64_t* n_accepted);
 
 /*
+ * Host only (no GPU needed): plan the tensor-core schedule of a Dense stack dims[0] -> ... -> dims[n_layers] (ReLU on all but the last
+ * layer) and replay its issue table against the epilogue's barrier arrivals for several tiles (phase parities, commit counts, k-step
+ * coverage).  Returns 0 when the stack has a consistent schedule, 1 when it does not fit the tensor-core kernel, 2 when the planner
+ * produced an inconsistent schedule (a bug); msg receives the reason.  Used by the CPU tests; mirrors nothing in the reference.
+ */
+int vae21_check_plan(int n_layers, const int* dims, char* msg, int msg_len);
+
+/*
  * Fused figure of merit (emulator.py:129-192 `error`, :409-439 `test_error`): err[i] = sqrt(mean_k (predict(params_i)[k] -
  * truth[i][k])^2) over the bins with band_mask[k] != 0 (NULL = all bins), in mK; with relative != 0 divided by max_k |truth[i][k]|
  * over the same bins and multiplied by 100 (%).  The 451-bin predictions never leave the GPU.  params / truth / err may each be
