@@ -1,0 +1,420 @@
+// FP32-SIMT fused emulator kernel, barrier-free variant ("pipe"): the same arithmetic as fp32_kernel.cuh -- every product an
+// fp32 FMA accumulated in k order (FFMA2 = two independent IEEE fmas), bias / ReLU / de-normalisation in the reference's rounding
+// order -- so its outputs are bit-identical to f32k::vae21_fp32_kernel; only the way weights reach the warps differs.
+//
+// Reference semantics: VeryAccurateEmulator/emulator.py:401-403, preprocess.py:49-110, :27-46.
+//
+// Why: in f32k every 8-k weight stage opens with `cp.async.wait_group` + `__syncthreads()`, and every layer ends with two more
+// block barriers.  With two warps per scheduler (226 registers) all eight warps then stall TOGETHER -- on the barrier, on the
+// first operand loads behind it, in every layer epilogue -- and nobody is left to keep the FMA pipe busy (ncu: FMA pipe 60 %).
+// But no warp ever needs another warp's data: warp w owns rows 8w..8w+7 of the tile through ALL layers (activations are
+// k-major `act[k][row]`, a warp reads and writes only its own 8-row column of them).  The only shared resource is the weight
+// stream.  So here
+//   * weights arrive through a ring of WST slots filled by 1-D bulk copies (`cp.async.bulk`, one per stage: a stage is KB
+//     consecutive rows of the host-packed [Kpad][Npad] image, i.e. contiguous) that complete on `full[slot]` mbarriers;
+//   * a warp waits for `full[slot]`, computes, and releases the slot with ONE arrival on `empty[slot]` (count 8);
+//   * there is no producer warp (a ninth warp would not fit the register file): stage g + DIST is issued by lane 0 of warp
+//     (g mod 8) when that warp opens its stage g, after waiting for `empty` of the slot's previous occupant, stage
+//     g + DIST - WST -- three stages behind for WST = 6, DIST = 3, so the wait is almost always over;
+//   * the stage stream runs on across layers and tiles (weights repeat per tile), warps drift apart by up to WST - DIST stages,
+//     and the epilogue / prologue of one warp overlaps the FMAs of the others.  Between layers only `__syncwarp()`;
+//   * a layer's outputs overwrite its inputs IN PLACE: a warp holds all outputs of its 8 rows in registers when the k loop ends
+//     and nobody else reads those rows, so ONE activation buffer (352 x 68 floats) replaces the two ping-pong buffers and the
+//     ring gets the space: 6 slots of 8 x 480 floats, 3 stages in flight, 3 stages of slack.
+// Deadlock freedom: the warp at the lowest stage m needs full[m], issued by warp (m - DIST) mod 8 on ENTERING its stage
+// m - DIST < m, which every warp has already done; that issue waited only for stage m - WST < m to be released.
+#pragma once
+#include "fp32_kernel.cuh"
+
+namespace f32p {
+
+using f32k::Layer;
+using f32k::Model;
+constexpr int MT = f32k::MT;
+constexpr int LDA = f32k::LDA;
+constexpr int NTHREADS = f32k::NTHREADS;
+constexpr int NWARPS = NTHREADS / 32;
+constexpr int KB = f32k::KB;         // k rows per stage
+constexpr int WST = 6;               // ring slots
+constexpr int DIST = 3;              // stages in flight ahead of a consumer
+constexpr int STAGE_FLOATS = KB * 32 * f32k::MAX_SLOTS;  // 8 rows of <= 480 columns
+constexpr int HEADER_BYTES = 1024;   // mbarriers + the layer table, ahead of the activation buffer
+
+struct Header {
+    unsigned long long full[WST];
+    unsigned long long empty[WST];
+    int nkb[VAE21_MAX_LAYERS];     // stages per layer
+    int sfloats[VAE21_MAX_LAYERS]; // floats per stage of the layer (KB x Npad)
+    Layer L[VAE21_MAX_LAYERS];
+};
+static_assert(sizeof(Header) <= HEADER_BYTES, "header");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    unsigned spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((++spins & 255u) == 0) {  // deadlock guard: a protocol bug must fault, not hang the GPU
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ll) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// Ring state of one thread (uniform across the CTA except for who is elected): the consumer position and the cursor of the next
+// stage to issue, which runs DIST stages ahead.
+struct Pipe {
+    uint32_t full0, empty0, ring0;  // shared-memory addresses
+    const float* ring;
+    const float* Wg;
+    const Header* hd;
+    int n_layers;
+    uint32_t cs, cph;  // consumer slot, parity of full[cs] to wait for
+    uint32_t g;        // stages consumed so far (mod 8 picks the issuing warp)
+    uint32_t ps, pph;  // producer slot, parity of empty[ps] to wait for (1 on a fresh barrier: passes at once)
+    // producer cursor: the packed weight image of a tile is ONE contiguous array ([Kpad][Npad] per layer, layers back to back), walked
+    // in steps of one stage
+    int pl, pk;        // layer, stages left in it
+    int psf;           // floats per stage of that layer
+    long long poff;    // float offset of the next stage
+    int pt;            // tiles left to issue (including the one the cursor is in)
+};
+
+__device__ __forceinline__ void issue_next(Pipe& p, bool elected) {
+    if (p.pt <= 0) return;
+    if (elected) {
+        const uint32_t bytes = static_cast<uint32_t>(p.psf) * 4u;
+        mbar_wait(p.empty0 + 8u * p.ps, p.pph);
+        mbar_expect_tx(p.full0 + 8u * p.ps, bytes);
+        bulk_g2s(p.ring0 + p.ps * (STAGE_FLOATS * 4u), p.Wg + p.poff, bytes, p.full0 + 8u * p.ps);
+    }
+    if (++p.ps == static_cast<uint32_t>(WST)) {
+        p.ps = 0;
+        p.pph ^= 1u;
+    }
+    p.poff += p.psf;
+    if (--p.pk == 0) {
+        if (++p.pl == p.n_layers) {
+            p.pl = 0;
+            p.poff = 0;
+            --p.pt;
+        }
+        p.pk = p.hd->nkb[p.pl];
+        p.psf = p.hd->sfloats[p.pl];
+    }
+}
+
+// One Dense layer for the warp's 8 rows of the tile, in place in the k-major activation buffer `act` (act[k][row], row stride LDA).
+template <int TN>
+__device__ __forceinline__ void run_layer(const Layer& L, bool last, const float* __restrict__ Bg, float* act, Pipe& p,
+                                          const NormConsts& nc, const LaunchArgs& a, long long row0) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Npad = L.Npad;
+    constexpr int KBL = KB;
+    const int nkb = L.Kpad / KBL;
+
+    // Column ownership of a lane (as in f32k, packed build): quads in each leading 128-column block, a pair in a 64-column block,
+    // at most one single column.  Slot j of the accumulator array is column col_of(j).
+    constexpr int NQ = TN >> 2, NS = TN & 3;
+    constexpr int NP = 2 * NQ + (NS >= 2 ? 1 : 0);
+    constexpr bool ODD = (NS & 1) != 0;
+    auto col_of = [&](int j) {
+        return j < 4 * NQ ? 128 * (j >> 2) + 4 * lane + (j & 3)
+                          : (j < 2 * NP ? 128 * NQ + 2 * lane + (j - 4 * NQ) : 128 * NQ + (NS >= 2 ? 64 : 0) + lane);
+    };
+
+    float2 acc2[8][NP > 0 ? NP : 1];
+    float acc1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        acc1[i] = 0.f;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) acc2[i][q] = make_float2(0.f, 0.f);
+    }
+
+    float bv[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) bv[j] = __ldg(Bg + L.b_off + col_of(j));
+
+    for (int kb = 0; kb < nkb; ++kb) {
+        issue_next(p, lane == 0 && static_cast<int>(p.g & (NWARPS - 1)) == warp);
+        mbar_wait(p.full0 + 8u * p.cs, p.cph);
+        const float* ws = p.ring + p.cs * STAGE_FLOATS;
+        const float* ap = act + (kb * KBL) * LDA + 8 * warp;
+#pragma unroll
+        for (int kk = 0; kk < KBL; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(ap + kk * LDA);
+            const float4 a1 = *reinterpret_cast<const float4*>(ap + kk * LDA + 4);
+            const float* wk = ws + kk * Npad;
+            float2 wp[NP > 0 ? NP : 1];
+            float w1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wk + 128 * q + 4 * lane);
+                wp[2 * q] = make_float2(w4.x, w4.y);
+                wp[2 * q + 1] = make_float2(w4.z, w4.w);
+            }
+            if (NS >= 2) wp[NP > 0 ? NP - 1 : 0] = *reinterpret_cast<const float2*>(wk + 128 * NQ + 2 * lane);
+            if (ODD) w1 = wk[128 * NQ + (NS >= 2 ? 64 : 0) + lane];
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float2 aa = make_float2(av[i], av[i]);
+#pragma unroll
+                for (int q = 0; q < NP; ++q) acc2[i][q] = __ffma2_rn(aa, wp[q], acc2[i][q]);
+                if (ODD) acc1[i] = fmaf(av[i], w1, acc1[i]);
+            }
+        }
+        __syncwarp();  // (also orders every lane's reads of `act` before the in-place stores of the epilogue)
+        if (lane == 0) mbar_arrive(p.empty0 + 8u * p.cs);  // every lane's reads of the slot have returned: release it
+        if (++p.cs == static_cast<uint32_t>(WST)) {
+            p.cs = 0;
+            p.cph ^= 1u;
+        }
+        ++p.g;
+    }
+
+    float acc[8][TN];  // register renaming only: slot j of the epilogues below is column col_of(j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            acc[i][2 * q] = acc2[i][q].x;
+            acc[i][2 * q + 1] = acc2[i][q].y;
+        }
+        if (ODD) acc[i][TN - 1] = acc1[i];
+    }
+
+    if (!last) {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = col_of(j);
+            const float b = bv[j];
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v[i] = __fadd_rn(acc[i][j], b);
+                if (L.relu) v[i] = v[i] < 0.f ? 0.f : v[i];  // NaN propagates like np.maximum / tf.nn.relu
+            }
+            float4* dst = reinterpret_cast<float4*>(act + n * LDA + 8 * warp);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    } else {
+        const int N = L.N;
+        const long long rbase = row0 + 8 * warp;
+        if (a.out_mode == OUT_CHI2) {
+            float part[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) part[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int n = col_of(j);
+                if (n < N) {
+                    const float b = bv[j], mu = __ldg(a.mu + n), ob = __ldg(a.obs + n), is = __ldg(a.isig + n);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float v = __fadd_rn(acc[i][j], b);
+                        if (L.relu) v = v < 0.f ? 0.f : v;
+                        v = __fadd_rn(__fmul_rn(v, nc.sd), mu);
+                        const float r = (v - ob) * is;
+                        part[i] = fmaf(r, r, part[i]);
+                    }
+                }
+            }
+            unsigned long long best = ~0ull;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float s = warp_sum(part[i]);
+                const long long row = rbase + i;
+                if (row < a.n) {
+                    if (a.chi2 && lane == 0) a.chi2[row] = s;
+                    const unsigned long long key = pack_min_key(s, static_cast<unsigned long long>(a.row_base + row));
+                    best = key < best ? key : best;
+                }
+            }
+            if (a.argmin_key && lane == 0 && best != ~0ull) atomicMin(a.argmin_key, best);
+        } else if (a.out_mode == OUT_ERROR) {
+            // fused emulator.py:129-192: rms difference to the row's true signal over the band, optionally in % of its amplitude
+            float part[8], amp[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) part[i] = amp[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int n = col_of(j);
+                if (n < N) {
+                    const float b = bv[j], mu = __ldg(a.mu + n), in_band = __ldg(a.isig + n);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const long long row = rbase + i;
+                        float v = __fadd_rn(acc[i][j], b);
+                        if (L.relu) v = v < 0.f ? 0.f : v;
+                        v = __fadd_rn(__fmul_rn(v, nc.sd), mu);
+                        const float t = row < a.n ? __ldg(a.truth + row * N + n) : 0.f;
+                        const float r = (v - t) * in_band;
+                        part[i] = fmaf(r, r, part[i]);
+                        amp[i] = fmaxf(amp[i], fabsf(t) * in_band);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float s = warp_sum(part[i]);
+                float m = amp[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                const long long row = rbase + i;
+                if (row < a.n && lane == 0) {
+                    float e = sqrtf(s * a.err_inv_count);
+                    if (a.err_relative) e = e / m * 100.f;
+                    a.chi2[row] = e;
+                }
+            }
+        } else {
+            const bool denorm = (a.out_mode == OUT_PREDICT);
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int n = col_of(j);
+                if (n < N) {
+                    const float b = bv[j];
+                    const float mu = denorm ? __ldg(a.mu + n) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const long long row = rbase + i;
+                        if (row < a.n) {
+                            float v = __fadd_rn(acc[i][j], b);
+                            if (L.relu) v = v < 0.f ? 0.f : v;
+                            if (denorm) v = __fadd_rn(__fmul_rn(v, nc.sd), mu);  // preprocess.py:44-45
+                            __stcs(a.out + row * N + n, v);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();  // the warp's activations are written before the next layer (or the next tile's prologue) touches them
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+vae21_fp32_pipe_kernel(const Model m, const NormConsts nc, const LaunchArgs a, const float* __restrict__ Wg,
+                       const float* __restrict__ Bg, const int act_rows) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Header* const hd = reinterpret_cast<Header*>(smem_raw);
+    float* const buf0 = reinterpret_cast<float*>(smem_raw + HEADER_BYTES);
+    float* const ring = buf0 + act_rows * LDA;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long ntiles = (a.n + MT - 1) / MT;
+    const int K0 = m.L[0].K, Kpad0 = m.L[0].Kpad;
+
+    if (tid < m.n_layers) {
+        hd->L[tid] = m.L[tid];
+        hd->nkb[tid] = m.L[tid].Kpad / KB;
+        hd->sfloats[tid] = KB * m.L[tid].Npad;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < WST; ++s) {
+            mbar_init(smem_u32(&hd->full[s]), 1);
+            mbar_init(smem_u32(&hd->empty[s]), NWARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    Pipe p;
+    p.full0 = smem_u32(&hd->full[0]);
+    p.empty0 = smem_u32(&hd->empty[0]);
+    p.ring0 = smem_u32(ring);
+    p.ring = ring;
+    p.Wg = Wg;
+    p.hd = hd;
+    p.n_layers = m.n_layers;
+    p.cs = 0;
+    p.cph = 0;
+    p.g = 0;
+    p.ps = 0;
+    p.pph = 1;
+    p.pl = 0;
+    p.pk = hd->nkb[0];
+    p.psf = hd->sfloats[0];
+    p.poff = 0;
+    p.pt = ntiles > blockIdx.x ? static_cast<int>((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+#pragma unroll
+    for (int s = 0; s < DIST; ++s) issue_next(p, tid == 0);  // the stages no consumer iteration issues
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long row0 = tile * MT;
+        // ---- prologue: the warp loads + transforms the parameters of ITS 8 rows into buf0[k][8w..8w+7] ----
+        const long long wrow0 = row0 + 8 * warp;
+        for (int e = lane; e < 8 * Kpad0; e += 32) {
+            int r, c;
+            float x = 0.f;
+            if (e < 8 * K0) {
+                r = e / K0;
+                c = e - r * K0;
+                const long long row = wrow0 + r;
+                if (row < a.n) {
+                    const long long gi = row * K0 + c;
+                    if (a.in_mode == IN_PARAMS_F64)
+                        x = transform_param(reinterpret_cast<const double*>(a.in)[gi], c, nc, false);
+                    else if (a.in_mode == IN_PARAMS_F32)
+                        x = transform_param(static_cast<double>(reinterpret_cast<const float*>(a.in)[gi]), c, nc, true);
+                    else if (a.in_mode == IN_GRID) {
+                        float xs[VAE21_MAX_PAR];
+                        grid_point(a, static_cast<unsigned long long>(a.row_base + row), K0, xs);
+                        x = xs[c];
+                    } else
+                        x = reinterpret_cast<const float*>(a.in)[gi];
+                }
+            } else {  // zero the k padding rows
+                const int e2 = e - 8 * K0;
+                c = K0 + (e2 >> 3);
+                r = e2 & 7;
+            }
+            buf0[c * LDA + 8 * warp + r] = x;
+        }
+        __syncwarp();
+
+        for (int l = 0; l < m.n_layers; ++l) {
+            const Layer& L = hd->L[l];
+            const bool last = (l == m.n_layers - 1);
+            const int slots = L.Npad >> 5;
+#define VAE21_CASE(T)                                          \
+    case T:                                                    \
+        run_layer<T>(L, last, Bg, buf0, p, nc, a, row0);       \
+        break;
+            switch (slots) {
+                VAE21_CASE(1) VAE21_CASE(2) VAE21_CASE(3) VAE21_CASE(4) VAE21_CASE(5)
+                VAE21_CASE(6) VAE21_CASE(7) VAE21_CASE(8) VAE21_CASE(9) VAE21_CASE(10)
+                VAE21_CASE(11) VAE21_CASE(12) VAE21_CASE(13) VAE21_CASE(14) VAE21_CASE(15)
+                default: break;
+            }
+#undef VAE21_CASE
+        }
+    }
+}
+
+}  // namespace f32p

@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "fp32_kernel.cuh"
+#include "fp32_pipe_kernel.cuh"
 #include "tc_kernel.cuh"
 
 namespace {
@@ -91,6 +92,9 @@ struct PinnedPool {
 };
 PinnedPool g_pool;
 
+#ifndef VAE21_FP32_PIPE_DEFAULT
+#define VAE21_FP32_PIPE_DEFAULT 0
+#endif
 constexpr int NSLOT = 3;              // pipeline depth of the host-buffer path
 constexpr long long CHUNK_ROWS = 32768;  // rows per pipeline chunk (59 MB of output)
 
@@ -108,6 +112,9 @@ struct vae21_handle {
     float* d_b32 = nullptr;
     size_t f32_smem = 0;
     int f32_wst = 3;
+    // barrier-free variant (fp32_pipe_kernel.cuh): rows of its single in-place activation buffer and its shared-memory bytes
+    int f32p_rows = 0;
+    size_t f32p_smem = 0;
     // tensor-core path
     tck::Plan tc{};
     bool tc_ok = false;
@@ -229,6 +236,9 @@ int pack_fp32(vae21_handle* h, const float* const* kernels, const float* const* 
         return fail(VAE21_ERR_UNSUPPORTED, "layer stack needs %zu B of activation shared memory (+%zu B/stage): too wide",
                     act, stage);
     h->f32_smem = act + h->f32_wst * stage;
+    h->f32p_rows = std::max(m.buf_rows[0], m.buf_rows[1]);
+    h->f32p_smem = f32p::HEADER_BYTES + static_cast<size_t>(h->f32p_rows) * f32k::LDA * sizeof(float) +
+                   static_cast<size_t>(f32p::WST) * f32p::STAGE_FLOATS * sizeof(float);  // <= 224 KB for any width <= 480
     if (h->d_w32) cudaFree(h->d_w32);
     if (h->d_b32) cudaFree(h->d_b32);
     h->d_w32 = h->d_b32 = nullptr;
@@ -238,6 +248,7 @@ int pack_fp32(vae21_handle* h, const float* const* kernels, const float* const* 
     CK(cudaMemcpy(h->d_b32, B.data(), B.size() * sizeof(float), cudaMemcpyHostToDevice));
     CK(cudaFuncSetAttribute(f32k::vae21_fp32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
     CK(cudaFuncSetAttribute(f32k::vae21_fp32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+    CK(cudaFuncSetAttribute(f32p::vae21_fp32_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
     return 0;
 }
 
@@ -245,7 +256,11 @@ int launch_fp32(vae21_handle* h, const LaunchArgs& a, cudaStream_t st) {
     const long long ntiles = (a.n + f32k::MT - 1) / f32k::MT;
     if (ntiles == 0) return 0;
     const int grid = (int)std::min<long long>(ntiles, h->sm_count);
-    if (h->f32_wst == 3)
+    // VAE21_FP32_PIPE=0 selects the block-barrier kernel (same bits; kept for A/B measurements and for stacks the ring does not fit)
+    static const int pipe_env = std::getenv("VAE21_FP32_PIPE") ? std::atoi(std::getenv("VAE21_FP32_PIPE")) : VAE21_FP32_PIPE_DEFAULT;
+    if (pipe_env && h->f32p_smem <= 227 * 1024)
+        f32p::vae21_fp32_pipe_kernel<<<grid, f32p::NTHREADS, h->f32p_smem, st>>>(h->f32, h->nc, a, h->d_w32, h->d_b32, h->f32p_rows);
+    else if (h->f32_wst == 3)
         f32k::vae21_fp32_kernel<3><<<grid, f32k::NTHREADS, h->f32_smem, st>>>(h->f32, h->nc, a, h->d_w32, h->d_b32);
     else
         f32k::vae21_fp32_kernel<2><<<grid, f32k::NTHREADS, h->f32_smem, st>>>(h->f32, h->nc, a, h->d_w32, h->d_b32);
