@@ -29,7 +29,7 @@ EXPORTS = [
     "vae21_set_model", "vae21_set_norm", "vae21_predict", "vae21_forward_normalised", "vae21_chi2", "vae21_chi2_grid", "vae21_error", "vae21_mcmc_run", "vae21_check_plan",
     "vae21_host_alloc", "vae21_host_free", "vae21_host_trim", "vae21_get_info", "vae21_get_tc_stats", "vae21_time_predict",
     "vae21_trainer_create", "vae21_trainer_destroy", "vae21_trainer_num_params", "vae21_trainer_set_params",
-    "vae21_trainer_get_params", "vae21_trainer_forward_backward", "vae21_trainer_adam", "vae21_trainer_epoch", "vae21_trainer_launches",
+    "vae21_trainer_get_params", "vae21_trainer_set_moments", "vae21_trainer_get_moments", "vae21_trainer_forward_backward", "vae21_trainer_adam", "vae21_trainer_epoch", "vae21_trainer_launches",
 ]
 
 
@@ -86,6 +86,8 @@ def load() -> C.CDLL:
         lib.vae21_trainer_num_params.argtypes = [vp, C.POINTER(i64)]
         lib.vae21_trainer_set_params.argtypes = [vp, f32p, i32]
         lib.vae21_trainer_get_params.argtypes = [vp, f32p]
+        lib.vae21_trainer_set_moments.argtypes = [vp, f32p, f32p]
+        lib.vae21_trainer_get_moments.argtypes = [vp, f32p, f32p]
         lib.vae21_trainer_forward_backward.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, vp, vp, vp]
         lib.vae21_trainer_adam.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp]
         lib.vae21_trainer_epoch.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float, i64, vp, vp]
@@ -441,6 +443,20 @@ class Trainer:
         out = np.empty(self.num_params, np.float32)
         _check(self._lib.vae21_trainer_get_params(self._t, out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
+
+    def set_moments(self, m, v):
+        """Adam first / second moments, flat in parameter order (host arrays)."""
+        m, v = np.ascontiguousarray(m, dtype=np.float32), np.ascontiguousarray(v, dtype=np.float32)
+        if m.size != self.num_params or v.size != self.num_params:
+            raise ValueError(f"expected {self.num_params} moments, got {m.size} / {v.size}")
+        fp = C.POINTER(C.c_float)
+        _check(self._lib.vae21_trainer_set_moments(self._t, m.ctypes.data_as(fp), v.ctypes.data_as(fp)))
+
+    def get_moments(self):
+        m, v = np.empty(self.num_params, np.float32), np.empty(self.num_params, np.float32)
+        fp = C.POINTER(C.c_float)
+        _check(self._lib.vae21_trainer_get_moments(self._t, m.ctypes.data_as(fp), v.ctypes.data_as(fp)))
+        return m, v
 
     @staticmethod
     def _dev_ptr(obj, dtype, what):

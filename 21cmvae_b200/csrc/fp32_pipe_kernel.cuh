@@ -59,25 +59,42 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {  // may suspend for a bounded time
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {  // never blocks
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// slow path of a wait, out of line: spin with a deadlock guard (a protocol bug must fault, not hang the GPU)
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     long long t0 = 0;
     unsigned spins = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) return;
-        if ((++spins & 255u) == 0) {  // deadlock guard: a protocol bug must fault, not hang the GPU
+    while (!mbar_try(bar, parity)) {
+        if ((++spins & 255u) == 0) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
             else if (now - t0 > 4000000000ll) __trap();
         }
     }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
@@ -94,6 +111,7 @@ struct Pipe {
     const Header* hd;
     int n_layers;
     uint32_t cs, cph;  // consumer slot, parity of full[cs] to wait for
+    uint32_t ready;    // full[cs] was already seen complete by the probe of the previous stage
     uint32_t g;        // stages consumed so far (mod 8 picks the issuing warp)
     uint32_t ps, pph;  // producer slot, parity of empty[ps] to wait for (1 on a fresh barrier: passes at once)
     // producer cursor: the packed weight image of a tile is ONE contiguous array ([Kpad][Npad] per layer, layers back to back), walked
@@ -133,7 +151,7 @@ template <int TN>
 __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float* __restrict__ Bg, float* act, Pipe& p,
                                           const NormConsts& nc, const LaunchArgs& a, long long row0) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int Npad = L.Npad;
+    constexpr int Npad = 32 * TN;  // == L.Npad (the dispatch below picks TN = L.Npad / 32): every weight address is an immediate
     constexpr int KBL = KB;
     const int nkb = L.Kpad / KBL;
 
@@ -162,7 +180,12 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
 
     for (int kb = 0; kb < nkb; ++kb) {
         issue_next(p, lane == 0 && static_cast<int>(p.g & (NWARPS - 1)) == warp);
-        mbar_wait(p.full0 + 8u * p.cs, p.cph);
+        if (!p.ready) mbar_wait(p.full0 + 8u * p.cs, p.cph);
+        {   // probe the NEXT stage's barrier now (non-blocking): its answer travels under this stage's FMAs, so that the usual
+            // hand-off costs no barrier round trip
+            const uint32_t ns = p.cs + 1 == static_cast<uint32_t>(WST) ? 0u : p.cs + 1;
+            p.ready = mbar_test(p.full0 + 8u * ns, ns ? p.cph : p.cph ^ 1u);
+        }
         const float* ws = p.ring + p.cs * STAGE_FLOATS;
         const float* ap = act + (kb * KBL) * LDA + 8 * warp;
 #pragma unroll
@@ -321,7 +344,7 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 vae21_fp32_pipe_kernel(const Model m, const NormConsts nc, const LaunchArgs a, const float* __restrict__ Wg,
-                       const float* __restrict__ Bg, const int act_rows) {
+                       const float* __restrict__ Bg, const int act_rows, const int skew) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Header* const hd = reinterpret_cast<Header*>(smem_raw);
     float* const buf0 = reinterpret_cast<float*>(smem_raw + HEADER_BYTES);
@@ -354,6 +377,7 @@ vae21_fp32_pipe_kernel(const Model m, const NormConsts nc, const LaunchArgs a, c
     p.n_layers = m.n_layers;
     p.cs = 0;
     p.cph = 0;
+    p.ready = 0;
     p.g = 0;
     p.ps = 0;
     p.pph = 1;
@@ -364,6 +388,14 @@ vae21_fp32_pipe_kernel(const Model m, const NormConsts nc, const LaunchArgs a, c
     p.pt = ntiles > blockIdx.x ? static_cast<int>((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 #pragma unroll
     for (int s = 0; s < DIST; ++s) issue_next(p, tid == 0);  // the stages no consumer iteration issues
+
+    // The two warps of a scheduler (w and w + 4) run the same instruction stream and, left alone, stay in lockstep: both reach the
+    // stage hand-off, the first operand loads and the epilogues in the same cycles and the FMA pipe idles meanwhile (measured: pipe
+    // busy 67 % = 2F / (2F + O) with F the FMA cycles of a warp's stage and O its other cycles).  Nothing pulls two de-phased warps
+    // back together (the ring has three stages of slack), so ONE delay of the upper four warps, once the ring is warm, puts a warp's
+    // overhead under its partner's FMAs for the rest of the launch.
+    bool skew_pending = warp >= NWARPS / 2 && skew > 0;
+    const int skew_layer = m.n_layers > 2 ? 2 : m.n_layers - 1;
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long row0 = tile * MT;
@@ -402,6 +434,12 @@ vae21_fp32_pipe_kernel(const Model m, const NormConsts nc, const LaunchArgs a, c
             const Layer& L = hd->L[l];
             const bool last = (l == m.n_layers - 1);
             const int slots = L.Npad >> 5;
+            if (skew_pending && l == skew_layer) {
+                const long long t0 = clock64();
+                while (clock64() - t0 < skew) {
+                }
+                skew_pending = false;
+            }
 #define VAE21_CASE(T)                                          \
     case T:                                                    \
         run_layer<T>(L, last, Bg, buf0, p, nc, a, row0);       \

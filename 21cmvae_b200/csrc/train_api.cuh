@@ -144,6 +144,24 @@ int vae21_trainer_get_params(vae21_trainer* t, float* flat_host) {
     return 0;
 }
 
+int vae21_trainer_set_moments(vae21_trainer* t, const float* m_host, const float* v_host) {
+    if (int rc = trainer_use(t)) return rc;
+    if (!m_host || !v_host) return fail(VAE21_ERR_ARG, "null moments");
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(t->m, m_host, sizeof(float) * t->n_params, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(t->v, v_host, sizeof(float) * t->n_params, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int vae21_trainer_get_moments(vae21_trainer* t, float* m_host, float* v_host) {
+    if (int rc = trainer_use(t)) return rc;
+    if (!m_host || !v_host) return fail(VAE21_ERR_ARG, "null output");
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(m_host, t->m, sizeof(float) * t->n_params, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(v_host, t->v, sizeof(float) * t->n_params, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 }  // extern "C"
 
 namespace {

@@ -288,10 +288,20 @@ class DirectEmulator:
         w = keras_h5.load_dense_chain(model_path)
         self.emulator = DenseModel(w, device=self.device)
         self._norm_for = None
+        # tf.keras.models.load_model returns the model COMPILED as it was saved (optimiser, its slot variables, the loss passed
+        # as custom object, emulator.py:334-337): restore that, so that load_model() + train() continues a training run
+        st = keras_h5.load_optimizer_state(model_path, w)
+        if st is not None:
+            from . import training as tr
+
+            self.emulator.compile(optimizer=tr.Adam.from_state(st), loss=None)
 
     def save_model(self, model_path):
-        """Write the current weights in the Keras-2.x HDF5 layout (loadable by ``load_model``)."""
-        keras_h5.save_dense_chain(model_path, self.emulator.weights)
+        """Write the current weights in the Keras-2.x HDF5 layout (loadable by ``load_model``), with the optimiser state of a
+        compiled model (``training_config`` + ``optimizer_weights``) like ``tf.keras.Model.save``."""
+        compiled = self.emulator._compiled or {}
+        opt = compiled.get("optimizer")
+        keras_h5.save_dense_chain(model_path, self.emulator.weights, optimizer=opt if hasattr(opt, "beta_1") else None)
 
     def save(self):
         raise NotImplementedError("Not implemented yet.")

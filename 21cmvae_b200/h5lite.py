@@ -403,7 +403,9 @@ class Writer:
 
     def create_dataset(self, path, data):
         node = self._node(path)
-        arr = np.ascontiguousarray(data)
+        arr = np.asarray(data)
+        if arr.ndim:  # (np.ascontiguousarray would turn a 0-d array -- Keras' `Adam/iter:0` -- into shape (1,))
+            arr = np.ascontiguousarray(arr)
         if arr.dtype.kind not in "fiu":
             raise H5LiteError("only numeric datasets supported")
         node.data = arr.astype(arr.dtype.newbyteorder("<"))

@@ -6,6 +6,10 @@ autoencoder-based emulator).  The architecture comes from the file's
 ``model_config`` attribute (not from ``hidden_dims``), exactly like the
 reference; weights come from ``model_weights/<layer>/<weight_names>``.
 
+The optimiser state Keras stores next to the weights (``training_config`` attribute + ``optimizer_weights`` group: Adam's
+iteration count and slot variables) is read by ``load_optimizer_state`` and written by ``save_dense_chain(..., optimizer=)``,
+so that a model retrained here continues where it stopped, as ``tf.keras.models.load_model`` + ``fit`` does in the reference.
+
 ``h5py`` is used when importable (the north-star loader); otherwise the
 dependency-free reader in ``h5lite`` parses the same files.
 """
@@ -71,6 +75,21 @@ class DenseChainWeights:
         )
         out.validate()
         return out
+
+
+@dataclass
+class AdamState:
+    """tf.keras.optimizers.Adam as a saved model carries it: hyper-parameters (``training_config``), ``Adam/iter:0`` and the
+    slot variables ``Adam/<layer>/{kernel,bias}/{m,v}:0``, here flat in ``get_weights()`` order (per layer kernel, then bias)."""
+
+    learning_rate: float = 0.001
+    beta_1: float = 0.9
+    beta_2: float = 0.999
+    epsilon: float = 1e-7
+    iterations: int = 0
+    m: Optional[np.ndarray] = None
+    v: Optional[np.ndarray] = None
+    loss: Optional[str] = None
 
 
 def _as_str(x) -> str:
@@ -158,12 +177,68 @@ def load_dense_chain(path: str) -> DenseChainWeights:
             f.close()
 
 
-def save_dense_chain(path: str, w: DenseChainWeights):
+def load_optimizer_state(path: str, w: Optional[DenseChainWeights] = None) -> Optional[AdamState]:
+    """The Adam state of a Keras full-model file, or None when the file has no ``training_config`` or was compiled with another
+    optimiser (such a model still predicts; it cannot be retrained here without an explicit ``compile``).  ``w``: the file's
+    weights (``load_dense_chain(path)``), read again when omitted."""
+    if w is None:
+        w = load_dense_chain(path)
+    f, via = _open(path)
+    try:
+        if "training_config" not in f.attrs:
+            return None
+        tc = json.loads(_as_str(f.attrs["training_config"]))
+        oc = tc.get("optimizer_config") or {}
+        if oc.get("class_name") != "Adam":
+            return None
+        c = oc.get("config", {})
+        if c.get("amsgrad"):
+            return None
+        loss = tc.get("loss")
+        st = AdamState(float(c.get("learning_rate", 0.001)), float(c.get("beta_1", 0.9)), float(c.get("beta_2", 0.999)),
+                       float(c.get("epsilon", 1e-7)), 0, None, None, loss if isinstance(loss, str) else None)
+        if "optimizer_weights" not in f:
+            return st
+        g = f["optimizer_weights"]
+        names = [_as_str(n) for n in np.asarray(g.attrs["weight_names"]).ravel()] if "weight_names" in g.attrs else []
+        slots = {}
+        for n in names:
+            obj = g
+            for part in n.split("/"):
+                obj = obj[part]
+            arr = _read_ds(obj, via)
+            parts = n.split("/")
+            if parts[-1].startswith("iter"):
+                st.iterations = int(np.asarray(arr).ravel()[0])
+            elif len(parts) >= 4 and parts[-1][:1] in ("m", "v"):
+                slots[(parts[-3], parts[-2], parts[-1][:1])] = np.asarray(arr, np.float32)
+        if slots:
+            flat = {"m": [], "v": []}
+            for ln, k, b in zip(w.layer_names, w.kernels, w.biases):
+                for which in ("m", "v"):
+                    sk, sb = slots.get((ln, "kernel", which)), slots.get((ln, "bias", which))
+                    if sk is None or sb is None or sk.shape != k.shape or sb.shape != b.shape:
+                        raise IOError(f"{path}: optimizer_weights lack Adam/{ln}/{{kernel,bias}}/{which}:0 of the model's shape")
+                    flat[which] += [sk.ravel(), sb.ravel()]
+            st.m, st.v = np.concatenate(flat["m"]), np.concatenate(flat["v"])
+        return st
+    except (KeyError, ValueError, h5lite.H5LiteError) as e:
+        raise IOError(f"{path}: unreadable optimizer state: {e}") from e
+    finally:
+        if via:
+            f.close()
+
+
+def save_dense_chain(path: str, w: DenseChainWeights, optimizer=None, loss: str = "loss_function"):
     """Write the Keras-2.x layout (model_config + model_weights) with h5lite.
 
     Files written here load back with ``load_dense_chain`` and follow the
     structure Keras 2.7 produces, so a TensorFlow
     installation can read them with ``load_model(..., compile=False)``.
+
+    ``optimizer``: an object with Adam's attributes (``AdamState`` / ``training.Adam``); its hyper-parameters go to the
+    ``training_config`` attribute and its iteration count and moments to ``optimizer_weights`` under the names Keras uses
+    (``loss`` is the name recorded there: the reference's models carry "loss_function", emulator.py:51-83).
     """
     w.validate()
     dims = w.dims
@@ -205,4 +280,25 @@ def save_dense_chain(path: str, w: DenseChainWeights):
         wr.create_dataset(f"/model_weights/{n}/{n}/kernel:0", np.asarray(k, np.float32))
         wr.create_dataset(f"/model_weights/{n}/{n}/bias:0", np.asarray(b, np.float32))
         wr.set_attr(f"/model_weights/{n}", "weight_names", [f"{n}/kernel:0", f"{n}/bias:0"])
+    if optimizer is not None:
+        f32 = lambda x: float(np.float32(x))  # noqa: E731 (Keras stores float32 hyper-parameters)
+        wr.set_attr("/", "training_config", json.dumps({
+            "loss": loss, "metrics": None, "weighted_metrics": None, "loss_weights": None,
+            "optimizer_config": {"class_name": "Adam", "config": {
+                "name": "Adam", "learning_rate": f32(optimizer.learning_rate), "decay": 0.0, "beta_1": f32(optimizer.beta_1),
+                "beta_2": f32(optimizer.beta_2), "epsilon": float(optimizer.epsilon), "amsgrad": False}}}))
+        m, v = getattr(optimizer, "m", None), getattr(optimizer, "v", None)
+        if m is not None and v is not None:
+            if np.size(m) != w.n_params() or np.size(v) != w.n_params():
+                raise ValueError("optimizer moments do not match the model's parameter count")
+            wnames = ["Adam/iter:0"]
+            wr.create_dataset("/optimizer_weights/Adam/iter:0", np.asarray(int(optimizer.iterations), dtype=np.int64))
+            for which, flat in (("m", np.asarray(m, np.float32).ravel()), ("v", np.asarray(v, np.float32).ravel())):
+                off = 0
+                for n, k, b in zip(names, w.kernels, w.biases):
+                    for part, ref in (("kernel", k), ("bias", b)):
+                        wr.create_dataset(f"/optimizer_weights/Adam/{n}/{part}/{which}:0", flat[off:off + ref.size].reshape(ref.shape))
+                        wnames.append(f"Adam/{n}/{part}/{which}:0")
+                        off += ref.size
+            wr.set_attr("/optimizer_weights", "weight_names", wnames)
     wr.save(path)

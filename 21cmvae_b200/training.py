@@ -35,6 +35,19 @@ class Adam:
         self.beta_2 = float(beta_2)
         self.epsilon = float(epsilon)
         self.iterations = 0
+        # slot variables (flat, parameter order) of the last fit: the next fit of the same model continues from them, as a
+        # Keras optimiser object does; keras_h5 stores / restores them (`optimizer_weights`)
+        self.m = None
+        self.v = None
+
+    @classmethod
+    def from_state(cls, st):
+        """From a ``keras_h5.AdamState`` (what ``load_model`` finds in a saved model)."""
+        opt = cls(st.learning_rate, st.beta_1, st.beta_2, st.epsilon)
+        opt.iterations = int(st.iterations)
+        opt.m = None if st.m is None else np.array(st.m, np.float32)
+        opt.v = None if st.v is None else np.array(st.v, np.float32)
+        return opt
 
 
 class Callback:
@@ -155,6 +168,10 @@ def fit(dims: Sequence[int], relu: Sequence[int], flat_params: np.ndarray, x, y,
         world, rank = dist.get_world_size(), dist.get_rank()
     tr = _lib.Trainer(dims, relu, max_batch=batch_size, device=device)
     tr.set_params(flat_params)
+    if optimizer.m is not None and optimizer.v is not None:
+        if np.size(optimizer.m) != tr.num_params or np.size(optimizer.v) != tr.num_params:
+            raise ValueError("the optimizer's moments belong to another model (parameter count differs)")
+        tr.set_moments(optimizer.m, optimizer.v)
     n, n_out = int(np.shape(x)[0]), int(dims[-1])
     as_dev = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev)  # noqa: E731
     dx, dy, dw = as_dev(x), as_dev(y), as_dev(w)
@@ -225,6 +242,7 @@ def fit(dims: Sequence[int], relu: Sequence[int], flat_params: np.ndarray, x, y,
     for cb in callbacks:
         cb.on_train_end(state)
     out = tr.get_params()
+    optimizer.m, optimizer.v = tr.get_moments()
     hist["kernel_launches"] = tr.launches()
     if timing is not None:
         hist["timing"] = timing

@@ -212,6 +212,10 @@ int vae21_trainer_destroy(vae21_trainer* t);
 int vae21_trainer_num_params(vae21_trainer* t, int64_t* n);
 int vae21_trainer_set_params(vae21_trainer* t, const float* flat_host, int reset_moments);
 int vae21_trainer_get_params(vae21_trainer* t, float* flat_host);
+/* Adam slot variables (first / second moment), flat in the order of the parameters: what Keras keeps in a saved model's
+ * `optimizer_weights` group (`Adam/<layer>/kernel/m:0` ...), so that a retrained model continues where it stopped. */
+int vae21_trainer_set_moments(vae21_trainer* t, const float* m_host, const float* v_host);
+int vae21_trainer_get_moments(vae21_trainer* t, float* m_host, float* v_host);
 int vae21_trainer_forward_backward(vae21_trainer* t, const float* x_all, const float* y_all, const float* w_all, const int* idx,
                                    int64_t first, int batch, float grad_scale, float* grad, float* loss_sum, void* stream);
 int vae21_trainer_adam(vae21_trainer* t, const float* grad, float lr_t, float beta1, float beta2, float eps, void* stream);

@@ -215,3 +215,77 @@ def test_load_model_takes_architecture_from_file(rm):
     e.load_model(os.path.join(GOLDEN, "tiny_keras.h5"))
     assert [l.units for l in e.emulator.layers] == [16, 24, 11]
     assert len(e.emulator.get_weights()) == 6
+
+
+# ---- optimiser state of a saved model (training_config + optimizer_weights, as tf.keras.Model.save writes them) ----
+def test_optimizer_state_round_trips_through_keras_h5(tmp_path, rm):
+    kh = pkg("keras_h5")
+    tr = pkg("training")
+    ks, bs, relu = rm.glorot_chain([7, 16, 12, 5], seed=4)
+    w = kh.DenseChainWeights(ks, bs, relu, ["hidden_0", "hidden_1", "out"], name="emulator")
+    rng = np.random.default_rng(0)
+    opt = tr.Adam(learning_rate=0.0123, beta_1=0.85, beta_2=0.97, epsilon=1e-6)
+    opt.iterations = 4321
+    opt.m = rng.normal(size=w.n_params()).astype(np.float32)
+    opt.v = rng.uniform(size=w.n_params()).astype(np.float32)
+    path = str(tmp_path / "with_opt.h5")
+    kh.save_dense_chain(path, w, optimizer=opt)
+    w2 = kh.load_dense_chain(path)
+    assert all(np.array_equal(a, b) for a, b in zip(w.kernels + w.biases, w2.kernels + w2.biases))
+    st = kh.load_optimizer_state(path, w2)
+    assert st is not None and st.iterations == 4321 and st.loss == "loss_function"
+    assert st.learning_rate == float(np.float32(0.0123)) and st.beta_1 == float(np.float32(0.85))
+    assert st.beta_2 == float(np.float32(0.97)) and st.epsilon == 1e-6
+    assert np.array_equal(st.m, opt.m) and np.array_equal(st.v, opt.v)
+    back = tr.Adam.from_state(st)
+    assert back.iterations == 4321 and np.array_equal(back.m, opt.m) and back.learning_rate == opt.learning_rate
+    # the file keeps Keras' names and shapes: iter is a 0-d int64, slots sit under Adam/<layer>/{kernel,bias}/{m,v}:0
+    f = pkg("h5lite").File(path)
+    names = [n.decode() if isinstance(n, bytes) else str(n) for n in np.asarray(f["optimizer_weights"].attrs["weight_names"]).ravel()]
+    assert names[0] == "Adam/iter:0" and names[1] == "Adam/hidden_0/kernel/m:0" and names[-1] == "Adam/out/bias/v:0"
+    it = f["optimizer_weights"]["Adam"]["iter:0"].read()
+    assert it.shape == () and it.dtype == np.int64
+    assert f["optimizer_weights"]["Adam"]["hidden_1"]["kernel"]["v:0"].read().shape == (16, 12)
+    # without an optimiser nothing is written and nothing is found
+    kh.save_dense_chain(path, w)
+    assert kh.load_optimizer_state(path) is None
+    # moments of another model are refused
+    opt.m = opt.m[:-1]
+    with pytest.raises(ValueError):
+        kh.save_dense_chain(path, w, optimizer=opt)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present")
+def test_reads_the_optimizer_state_of_the_shipped_models():
+    """ae_emulator.h5 was saved by Keras 2.7 after training: Adam(lr 2.78e-4 after ReduceLROnPlateau), slots for its 5 layers."""
+    kh = pkg("keras_h5")
+    base = REFERENCE + "/VeryAccurateEmulator/models/autoencoder_based_emulator/"
+    w = kh.load_dense_chain(base + "ae_emulator.h5")
+    st = kh.load_optimizer_state(base + "ae_emulator.h5", w)
+    assert st is not None and st.loss == "mean_squared_error" and st.iterations > 0
+    assert abs(st.learning_rate - 0.00027812839834950864) < 1e-12 and st.epsilon == 1e-7
+    assert st.m.shape == st.v.shape == (w.n_params(),) and np.all(st.v >= 0) and np.any(st.m != 0)
+    assert kh.load_optimizer_state(base + "decoder.h5") is None  # saved without compile
+
+
+def test_load_model_restores_the_compiled_optimizer(tmp_path, rm):
+    """tf.keras.models.load_model returns the model compiled as saved (emulator.py:334-337); save_model writes that state."""
+    emu = pkg("emulator")
+    pp = pkg("preprocess")
+    kh = pkg("keras_h5")
+    tr = pkg("training")
+    ks, bs, relu = rm.glorot_chain([7, 8, 451], seed=9)
+    pmin, pmax = rm.prior_par_stats()
+    stats = pp.NormStats(pmin, pmax, np.zeros(451, np.float32), np.float32(1.0))
+    e = emu.DirectEmulator(stats=stats)
+    e.emulator = emu.DenseModel(kh.DenseChainWeights(ks, bs, relu, name="emulator"))
+    opt = tr.Adam(0.005)
+    opt.iterations, opt.m, opt.v = 77, np.full(e.emulator.weights.n_params(), 0.5, np.float32), np.full(e.emulator.weights.n_params(), 0.25, np.float32)
+    e.emulator.compile(optimizer=opt, loss=None)
+    path = str(tmp_path / "m.h5")
+    e.save_model(path)
+    e2 = emu.DirectEmulator(stats=stats)
+    e2.load_model(path)
+    got = e2.emulator._compiled["optimizer"]
+    assert isinstance(got, tr.Adam) and got.iterations == 77 and got.learning_rate == float(np.float32(0.005))
+    assert np.array_equal(got.m, opt.m) and np.array_equal(got.v, opt.v)

@@ -295,3 +295,35 @@ def test_epoch_call_equals_per_batch_calls(rm):
     b.epoch(dx, dy, dw, perm, n, batch, lr, 0.9, 0.999, 1e-7, 0, lb)
     assert np.array_equal(a.get_params(), b.get_params())
     assert float(la.item()) == float(lb.item())
+
+
+@pytest.mark.gpu
+def test_fit_continues_from_the_optimizers_saved_state(rm, tmp_path):
+    """Two epochs in one fit == one epoch, save (weights + training_config + optimizer_weights), load, one more epoch: the Adam
+    moments and the iteration count travel through the Keras HDF5 file, like tf.keras.Model.save / load_model + fit."""
+    tr = pkg("training")
+    kh = pkg("keras_h5")
+    dims, n = (7, 40, 24, 451), 64 * 3 + 17
+    ks, bs, relu, x, y, mos = _problem(dims, n, 5, rm)
+    from oracle import train_ref as tref
+
+    w = tref.sample_weights(y, mos).astype(np.float32)
+    flat0 = tr.flatten_weights(ks, bs)
+    one = tr.Adam(0.01)
+    ref, _ = tr.fit(dims, relu, flat0, x, y, w, optimizer=one, epochs=2, batch_size=64, shuffle=False)
+    opt = tr.Adam(0.01)
+    half, _ = tr.fit(dims, relu, flat0, x, y, w, optimizer=opt, epochs=1, batch_size=64, shuffle=False)
+    assert opt.iterations == 4 and opt.m is not None and np.any(opt.m != 0)
+    k1, b1 = tr.unflatten_weights(half, dims)
+    path = str(tmp_path / "half.h5")
+    kh.save_dense_chain(path, kh.DenseChainWeights(k1, b1, [bool(r) for r in relu], name="emulator"), optimizer=opt)
+    w2 = kh.load_dense_chain(path)
+    opt2 = tr.Adam.from_state(kh.load_optimizer_state(path, w2))
+    assert opt2.iterations == 4 and np.array_equal(opt2.m, opt.m) and np.array_equal(opt2.v, opt.v)
+    done, _ = tr.fit(dims, relu, tr.flatten_weights(w2.kernels, w2.biases), x, y, w, optimizer=opt2, epochs=1, batch_size=64, shuffle=False)
+    assert opt2.iterations == 8 == one.iterations
+    assert np.array_equal(done, ref)
+    assert np.array_equal(opt2.m, one.m) and np.array_equal(opt2.v, one.v)
+    # and a fresh optimiser (moments reset) does NOT reproduce it: the state matters
+    cold, _ = tr.fit(dims, relu, tr.flatten_weights(w2.kernels, w2.biases), x, y, w, optimizer=tr.Adam(0.01), epochs=1, batch_size=64, shuffle=False)
+    assert not np.array_equal(cold, ref)
