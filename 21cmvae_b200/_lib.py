@@ -29,7 +29,8 @@ EXPORTS = [
     "vae21_set_model", "vae21_set_norm", "vae21_predict", "vae21_forward_normalised", "vae21_chi2", "vae21_chi2_grid", "vae21_error", "vae21_mcmc_run", "vae21_check_plan",
     "vae21_host_alloc", "vae21_host_free", "vae21_host_trim", "vae21_get_info", "vae21_get_tc_stats", "vae21_time_predict",
     "vae21_trainer_create", "vae21_trainer_destroy", "vae21_trainer_num_params", "vae21_trainer_set_params",
-    "vae21_trainer_get_params", "vae21_trainer_set_moments", "vae21_trainer_get_moments", "vae21_trainer_forward_backward", "vae21_trainer_adam", "vae21_trainer_epoch", "vae21_trainer_launches",
+    "vae21_trainer_get_params", "vae21_trainer_set_moments", "vae21_trainer_get_moments", "vae21_trainer_forward_backward", "vae21_trainer_adam", "vae21_trainer_epoch", "vae21_trainer_dp_begin", "vae21_trainer_dp_forward_backward", "vae21_trainer_dp_adam",
+    "vae21_trainer_launches",
 ]
 
 
@@ -91,6 +92,9 @@ def load() -> C.CDLL:
         lib.vae21_trainer_forward_backward.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, vp, vp, vp]
         lib.vae21_trainer_adam.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp]
         lib.vae21_trainer_epoch.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float, i64, vp, vp]
+        lib.vae21_trainer_dp_begin.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, i64, vp, vp, vp]
+        lib.vae21_trainer_dp_forward_backward.argtypes = [vp, vp]
+        lib.vae21_trainer_dp_adam.argtypes = [vp, vp]
         lib.vae21_trainer_launches.argtypes = [vp, C.POINTER(i64)]
         for name in EXPORTS:  # a stale libvae21.so must fail here, not at first use
             getattr(lib, name)
@@ -481,6 +485,22 @@ class Trainer:
     def adam(self, grad, lr_t, beta1=0.9, beta2=0.999, eps=1e-7, stream=None):
         _check(self._lib.vae21_trainer_adam(self._t, self._dev_ptr(grad, np.float32, "grad"), float(lr_t), float(beta1),
                                             float(beta2), float(eps), C.c_void_p(int(stream)) if stream else None))
+
+    def dp_begin(self, x_all, y_all, w_all, perm, n, batch, share_first, share_rows, lr, beta1, beta2, eps, iterations_before, grad,
+                 loss_sum, stream=None):
+        """Prepare a data-parallel epoch on this rank (see vae21_trainer_dp_begin): two graphs around the caller's all-reduce."""
+        _check(self._lib.vae21_trainer_dp_begin(
+            self._t, self._dev_ptr(x_all, np.float32, "x_all"), self._dev_ptr(y_all, np.float32, "y_all"),
+            self._dev_ptr(w_all, np.float32, "w_all"), self._dev_ptr(perm, np.int32, "perm"), int(n), int(batch), int(share_first),
+            int(share_rows), float(lr), float(beta1), float(beta2), float(eps), int(iterations_before),
+            self._dev_ptr(grad, np.float32, "grad"), self._dev_ptr(loss_sum, np.float32, "loss_sum"),
+            C.c_void_p(int(stream)) if stream else None))
+
+    def dp_forward_backward(self, stream=None):
+        _check(self._lib.vae21_trainer_dp_forward_backward(self._t, C.c_void_p(int(stream)) if stream else None))
+
+    def dp_adam(self, stream=None):
+        _check(self._lib.vae21_trainer_dp_adam(self._t, C.c_void_p(int(stream)) if stream else None))
 
     def epoch(self, x_all, y_all, w_all, perm, n, batch, lr, beta1, beta2, eps, iterations_before, loss_sum, stream=None):
         """All batches of one epoch in one library call (single GPU); see vae21_trainer_epoch."""

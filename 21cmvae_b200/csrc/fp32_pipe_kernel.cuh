@@ -38,14 +38,14 @@ constexpr int KB = f32k::KB;         // k rows per stage
 constexpr int WST = 6;               // ring slots
 constexpr int DIST = 3;              // stages in flight ahead of a consumer
 constexpr int STAGE_FLOATS = KB * 32 * f32k::MAX_SLOTS;  // 8 rows of <= 480 columns
-constexpr int HEADER_BYTES = 1024;   // mbarriers + the layer table, ahead of the activation buffer
+constexpr int HEADER_BYTES = 4096;   // mbarriers + the layer table + the stage table, ahead of the activation buffer
+constexpr int MAX_STAGES = 400;      // stages of one tile (DirectEmulator 145, AE chain 211); wider stacks use the block-barrier kernel
 
 struct Header {
     unsigned long long full[WST];
     unsigned long long empty[WST];
-    int nkb[VAE21_MAX_LAYERS];     // stages per layer
-    int sfloats[VAE21_MAX_LAYERS]; // floats per stage of the layer (KB x Npad)
     Layer L[VAE21_MAX_LAYERS];
+    uint2 stage[MAX_STAGES];       // per stage of a tile: {float offset into the packed weight image, bytes}
 };
 static_assert(sizeof(Header) <= HEADER_BYTES, "header");
 
@@ -102,48 +102,39 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  : "memory");
 }
 
-// Ring state of one thread (uniform across the CTA except for who is elected): the consumer position and the cursor of the next
-// stage to issue, which runs DIST stages ahead.
+// Ring state of one thread (uniform across the CTA): the consumer position and the cursor of the next stage to issue, which runs
+// DIST stages ahead.  The packed weight image of a tile is one contiguous array ([Kpad][Npad] per layer, layers back to back); the
+// stage table in shared memory holds {offset, bytes} of each of its S stages, so the cursor is an index.
 struct Pipe {
     uint32_t full0, empty0, ring0;  // shared-memory addresses
     const float* ring;
     const float* Wg;
-    const Header* hd;
-    int n_layers;
+    const uint2* tab;
+    int S;             // stages per tile
     uint32_t cs, cph;  // consumer slot, parity of full[cs] to wait for
     uint32_t ready;    // full[cs] was already seen complete by the probe of the previous stage
     uint32_t g;        // stages consumed so far (mod 8 picks the issuing warp)
     uint32_t ps, pph;  // producer slot, parity of empty[ps] to wait for (1 on a fresh barrier: passes at once)
-    // producer cursor: the packed weight image of a tile is ONE contiguous array ([Kpad][Npad] per layer, layers back to back), walked
-    // in steps of one stage
-    int pl, pk;        // layer, stages left in it
-    int psf;           // floats per stage of that layer
-    long long poff;    // float offset of the next stage
+    int pidx;          // producer cursor: stage of the tile
     int pt;            // tiles left to issue (including the one the cursor is in)
 };
 
-__device__ __forceinline__ void issue_next(Pipe& p, bool elected) {
-    if (p.pt <= 0) return;
-    if (elected) {
-        const uint32_t bytes = static_cast<uint32_t>(p.psf) * 4u;
-        mbar_wait(p.empty0 + 8u * p.ps, p.pph);
-        mbar_expect_tx(p.full0 + 8u * p.ps, bytes);
-        bulk_g2s(p.ring0 + p.ps * (STAGE_FLOATS * 4u), p.Wg + p.poff, bytes, p.full0 + 8u * p.ps);
+// The whole warp waits for the slot (no divergence to reconverge from), lane 0 issues the copy.
+__device__ __forceinline__ void issue_stage(const Pipe& p, bool lane0) {
+    const uint2 e = p.tab[p.pidx];
+    mbar_wait(p.empty0 + 8u * p.ps, p.pph);
+    if (lane0) {
+        mbar_expect_tx(p.full0 + 8u * p.ps, e.y);
+        bulk_g2s(p.ring0 + p.ps * (STAGE_FLOATS * 4u), p.Wg + e.x, e.y, p.full0 + 8u * p.ps);
     }
-    if (++p.ps == static_cast<uint32_t>(WST)) {
-        p.ps = 0;
-        p.pph ^= 1u;
-    }
-    p.poff += p.psf;
-    if (--p.pk == 0) {
-        if (++p.pl == p.n_layers) {
-            p.pl = 0;
-            p.poff = 0;
-            --p.pt;
-        }
-        p.pk = p.hd->nkb[p.pl];
-        p.psf = p.hd->sfloats[p.pl];
-    }
+}
+__device__ __forceinline__ void advance_cursor(Pipe& p) {  // branch-free; harmless once pt has reached 0
+    const bool wrap_s = p.ps + 1 == static_cast<uint32_t>(WST);
+    p.ps = wrap_s ? 0u : p.ps + 1;
+    p.pph ^= wrap_s ? 1u : 0u;
+    const bool wrap_t = p.pidx + 1 == p.S;
+    p.pidx = wrap_t ? 0 : p.pidx + 1;
+    p.pt -= wrap_t ? 1 : 0;
 }
 
 // One Dense layer for the warp's 8 rows of the tile, in place in the k-major activation buffer `act` (act[k][row], row stride LDA).
@@ -179,8 +170,14 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
     for (int j = 0; j < TN; ++j) bv[j] = __ldg(Bg + L.b_off + col_of(j));
 
     for (int kb = 0; kb < nkb; ++kb) {
-        issue_next(p, lane == 0 && static_cast<int>(p.g & (NWARPS - 1)) == warp);
-        if (!p.ready) mbar_wait(p.full0 + 8u * p.cs, p.cph);
+        // hand-off: ONE rarely taken branch in the common path (this warp's turn to issue comes every 8th stage; the stage's data
+        // has usually been seen by the previous stage's probe)
+        const bool mine = static_cast<int>(p.g & (NWARPS - 1)) == warp && p.pt > 0;
+        if (mine || !p.ready) {
+            if (mine) issue_stage(p, lane == 0);
+            if (!p.ready) mbar_wait(p.full0 + 8u * p.cs, p.cph);
+        }
+        advance_cursor(p);
         {   // probe the NEXT stage's barrier now (non-blocking): its answer travels under this stage's FMAs, so that the usual
             // hand-off costs no barrier round trip
             const uint32_t ns = p.cs + 1 == static_cast<uint32_t>(WST) ? 0u : p.cs + 1;
@@ -214,9 +211,10 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
         }
         __syncwarp();  // (also orders every lane's reads of `act` before the in-place stores of the epilogue)
         if (lane == 0) mbar_arrive(p.empty0 + 8u * p.cs);  // every lane's reads of the slot have returned: release it
-        if (++p.cs == static_cast<uint32_t>(WST)) {
-            p.cs = 0;
-            p.cph ^= 1u;
+        {
+            const bool wrap = p.cs + 1 == static_cast<uint32_t>(WST);
+            p.cs = wrap ? 0u : p.cs + 1;
+            p.cph ^= wrap ? 1u : 0u;
         }
         ++p.g;
     }
@@ -344,7 +342,7 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 vae21_fp32_pipe_kernel(const Model m, const NormConsts nc, const LaunchArgs a, const float* __restrict__ Wg,
-                       const float* __restrict__ Bg, const int act_rows, const int skew) {
+                       const float* __restrict__ Bg, const int act_rows, const int n_stages) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Header* const hd = reinterpret_cast<Header*>(smem_raw);
     float* const buf0 = reinterpret_cast<float*>(smem_raw + HEADER_BYTES);
@@ -355,8 +353,11 @@ vae21_fp32_pipe_kernel(const Model m, const NormConsts nc, const LaunchArgs a, c
 
     if (tid < m.n_layers) {
         hd->L[tid] = m.L[tid];
-        hd->nkb[tid] = m.L[tid].Kpad / KB;
-        hd->sfloats[tid] = KB * m.L[tid].Npad;
+        int first = 0;  // stages of the layers before this one
+        for (int l = 0; l < tid; ++l) first += m.L[l].Kpad / KB;
+        const unsigned sf = static_cast<unsigned>(KB * m.L[tid].Npad);
+        for (int kb = 0; kb < m.L[tid].Kpad / KB; ++kb)
+            hd->stage[first + kb] = make_uint2(static_cast<unsigned>(m.L[tid].w_off) + kb * sf, sf * 4u);
     }
     if (tid == 0) {
         for (int s = 0; s < WST; ++s) {
@@ -373,29 +374,21 @@ vae21_fp32_pipe_kernel(const Model m, const NormConsts nc, const LaunchArgs a, c
     p.ring0 = smem_u32(ring);
     p.ring = ring;
     p.Wg = Wg;
-    p.hd = hd;
-    p.n_layers = m.n_layers;
+    p.tab = hd->stage;
+    p.S = n_stages;
     p.cs = 0;
     p.cph = 0;
     p.ready = 0;
     p.g = 0;
     p.ps = 0;
     p.pph = 1;
-    p.pl = 0;
-    p.pk = hd->nkb[0];
-    p.psf = hd->sfloats[0];
-    p.poff = 0;
+    p.pidx = 0;
     p.pt = ntiles > blockIdx.x ? static_cast<int>((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 #pragma unroll
-    for (int s = 0; s < DIST; ++s) issue_next(p, tid == 0);  // the stages no consumer iteration issues
-
-    // The two warps of a scheduler (w and w + 4) run the same instruction stream and, left alone, stay in lockstep: both reach the
-    // stage hand-off, the first operand loads and the epilogues in the same cycles and the FMA pipe idles meanwhile (measured: pipe
-    // busy 67 % = 2F / (2F + O) with F the FMA cycles of a warp's stage and O its other cycles).  Nothing pulls two de-phased warps
-    // back together (the ring has three stages of slack), so ONE delay of the upper four warps, once the ring is warm, puts a warp's
-    // overhead under its partner's FMAs for the rest of the launch.
-    bool skew_pending = warp >= NWARPS / 2 && skew > 0;
-    const int skew_layer = m.n_layers > 2 ? 2 : m.n_layers - 1;
+    for (int s = 0; s < DIST; ++s) {  // the stages no consumer iteration issues
+        if (warp == 0 && p.pt > 0) issue_stage(p, lane == 0);
+        advance_cursor(p);
+    }
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long row0 = tile * MT;
@@ -434,12 +427,6 @@ vae21_fp32_pipe_kernel(const Model m, const NormConsts nc, const LaunchArgs a, c
             const Layer& L = hd->L[l];
             const bool last = (l == m.n_layers - 1);
             const int slots = L.Npad >> 5;
-            if (skew_pending && l == skew_layer) {
-                const long long t0 = clock64();
-                while (clock64() - t0 < skew) {
-                }
-                skew_pending = false;
-            }
 #define VAE21_CASE(T)                                          \
     case T:                                                    \
         run_layer<T>(L, last, Bg, buf0, p, nc, a, row0);       \

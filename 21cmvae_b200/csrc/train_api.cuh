@@ -33,6 +33,13 @@ struct vae21_trainer {
     long long lr_cap = 0;
     int* d_step = nullptr;
     float* d_loss = nullptr;
+    // data-parallel step as TWO replayable graphs around the caller's gradient all-reduce (vae21_trainer_dp_*): A = gather of this
+    // rank's share of the step's batch + forward + loss + backward into the caller's gradient buffer, B = Adam + step counter
+    cudaGraphExec_t dpA = nullptr, dpB = nullptr;
+    const void *dp_x = nullptr, *dp_y = nullptr, *dp_w = nullptr, *dp_grad = nullptr, *dp_loss = nullptr;
+    int dp_batch = 0, dp_first = 0, dp_rows = 0;
+    float dp_b1 = 0, dp_b2 = 0, dp_eps = 0;
+    long long dpA_kernels = 0, dp_steps = 0;
     long long launches = 0;
 };
 
@@ -110,6 +117,8 @@ int vae21_trainer_destroy(vae21_trainer* t) {
     for (int i = 0; i < 2; ++i)
         if (t->throttle[i]) cudaEventDestroy(t->throttle[i]);
     if (t->gexec) cudaGraphExecDestroy(t->gexec);
+    if (t->dpA) cudaGraphExecDestroy(t->dpA);
+    if (t->dpB) cudaGraphExecDestroy(t->dpB);
     if (t->gstream) cudaStreamDestroy(t->gstream);
     if (t->ev_in) cudaEventDestroy(t->ev_in);
     if (t->ev_out) cudaEventDestroy(t->ev_out);
@@ -167,9 +176,10 @@ int vae21_trainer_get_moments(vae21_trainer* t, float* m_host, float* v_host) {
 namespace {
 // forward + loss (+ backward when grad != nullptr) of one batch; step != nullptr: graph form (batch number read on the device)
 int enqueue_step(vae21_trainer* t, const float* x_all, const float* y_all, const float* w_all, const int* idx, int64_t first, int batch,
-                 float grad_scale, float* grad, float* loss_sum, cudaStream_t st, const int* step) {
+                 float grad_scale, float* grad, float* loss_sum, cudaStream_t st, const int* step, int stride = 0) {
     const int L = t->n_layers, NO = t->dims[L];
-    trk::gather_kernel<<<batch, 128, 0, st>>>(x_all, y_all, w_all, idx, first, batch, t->dims[0], NO, t->act[0], t->yb, t->wb, step);
+    trk::gather_kernel<<<batch, 128, 0, st>>>(x_all, y_all, w_all, idx, first, batch, t->dims[0], NO, t->act[0], t->yb, t->wb, step,
+                                              stride ? stride : batch);
     trainer_forward(t, batch, st);
     float* d_cur = t->delta[0];
     trk::loss_delta_kernel<<<(batch + 7) / 8, 256, 0, st>>>(t->act[L], t->yb, t->wb, batch, NO, grad_scale, grad ? d_cur : nullptr, t->loss_rows);
@@ -312,6 +322,109 @@ int vae21_trainer_epoch(vae21_trainer* t, const float* x_all, const float* y_all
     CK(cudaGetLastError());
     CK(cudaEventRecord(t->ev_out, gs));
     CK(cudaStreamWaitEvent(ust, t->ev_out, 0));
+    return 0;
+}
+
+int vae21_trainer_dp_begin(vae21_trainer* t, const float* x_all, const float* y_all, const float* w_all, const int* perm, int64_t n, int batch,
+                           int share_first, int share_rows, float lr, float beta1, float beta2, float eps, int64_t iterations_before,
+                           float* grad, float* loss_sum, void* stream) {
+    if (int rc = trainer_use(t)) return rc;
+    if (!x_all || !y_all || !w_all || !perm || !grad || !loss_sum) return fail(VAE21_ERR_ARG, "null device pointer");
+    if (n < 0 || batch < 1 || share_first < 0 || share_rows < 0 || share_first + share_rows > batch || share_rows > t->max_batch)
+        return fail(VAE21_ERR_ARG, "bad n / batch / share");
+    const int NO = t->dims[t->n_layers];
+    cudaStream_t ust = static_cast<cudaStream_t>(stream);
+    const int64_t n_full = n / batch;
+    auto drop = [&]() {
+        if (t->dpA) { cudaGraphExecDestroy(t->dpA); t->dpA = nullptr; }
+        if (t->dpB) { cudaGraphExecDestroy(t->dpB); t->dpB = nullptr; }
+    };
+    if (t->perm_cap < n) {
+        CK(cudaStreamSynchronize(ust));
+        if (t->d_perm) cudaFree(t->d_perm);
+        t->d_perm = nullptr;
+        CK(cudaMalloc(&t->d_perm, sizeof(int) * std::max<int64_t>(n, 1)));
+        t->perm_cap = n;
+        drop();
+        if (t->gexec) { cudaGraphExecDestroy(t->gexec); t->gexec = nullptr; }
+    }
+    if (t->lr_cap < n_full) {
+        CK(cudaStreamSynchronize(ust));
+        if (t->d_lr) cudaFree(t->d_lr);
+        t->d_lr = nullptr;
+        CK(cudaMalloc(&t->d_lr, sizeof(float) * std::max<int64_t>(n_full, 1)));
+        t->lr_cap = n_full;
+        drop();
+        if (t->gexec) { cudaGraphExecDestroy(t->gexec); t->gexec = nullptr; }
+    }
+    CK(cudaMemcpyAsync(t->d_perm, perm, sizeof(int) * n, cudaMemcpyDeviceToDevice, ust));
+    std::vector<float> lrs(std::max<int64_t>(n_full, 1));
+    for (int64_t k = 0; k < n_full; ++k)
+        lrs[k] = static_cast<float>(static_cast<double>(lr) * std::sqrt(1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(iterations_before + k + 1))) /
+                                    (1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(iterations_before + k + 1))));
+    CK(cudaMemcpyAsync(t->d_lr, lrs.data(), sizeof(float) * n_full, cudaMemcpyHostToDevice, ust));
+    CK(cudaMemsetAsync(t->d_step, 0, sizeof(int), ust));
+    CK(cudaStreamSynchronize(ust));  // `lrs` is pageable host memory
+    t->dp_steps = n_full;
+    const bool same = t->dpB && t->dp_x == x_all && t->dp_y == y_all && t->dp_w == w_all && t->dp_grad == grad && t->dp_loss == loss_sum &&
+                      t->dp_batch == batch && t->dp_first == share_first && t->dp_rows == share_rows && t->dp_b1 == beta1 && t->dp_b2 == beta2 &&
+                      t->dp_eps == eps;
+    if (same) return 0;
+    drop();
+    cudaStream_t gs = t->gstream;
+    const long long launches_before = t->launches;
+    if (share_rows > 0) {
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_step(t, x_all, y_all, w_all, t->d_perm, share_first, share_rows, static_cast<float>(1.0 / (static_cast<double>(NO) * batch)),
+                                    grad, loss_sum, gs, t->d_step, batch);
+        const cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+        if (rc != 0 || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            t->launches = launches_before;
+            return rc ? rc : fail(VAE21_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&t->dpA, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) return fail(VAE21_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(ie));
+    }
+    t->dpA_kernels = t->launches - launches_before;
+    t->launches = launches_before;  // capturing launched nothing
+    {
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_adam(t, grad, 0.f, beta1, beta2, eps, gs, t->d_lr, t->d_step);
+        trk::step_inc_kernel<<<1, 1, 0, gs>>>(t->d_step);
+        const cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+        t->launches = launches_before;
+        if (rc != 0 || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            drop();
+            return rc ? rc : fail(VAE21_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&t->dpB, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { drop(); return fail(VAE21_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(ie)); }
+    }
+    t->dp_x = x_all; t->dp_y = y_all; t->dp_w = w_all; t->dp_grad = grad; t->dp_loss = loss_sum;
+    t->dp_batch = batch; t->dp_first = share_first; t->dp_rows = share_rows; t->dp_b1 = beta1; t->dp_b2 = beta2; t->dp_eps = eps;
+    return 0;
+}
+
+int vae21_trainer_dp_forward_backward(vae21_trainer* t, void* stream) {
+    if (int rc = trainer_use(t)) return rc;
+    if (!t->dpB) return fail(VAE21_ERR_STATE, "vae21_trainer_dp_begin has not been called");
+    if (!t->dpA) return fail(VAE21_ERR_STATE, "this rank has no rows in a batch (zero its gradient instead)");
+    CK(cudaGraphLaunch(t->dpA, static_cast<cudaStream_t>(stream)));
+    t->launches += t->dpA_kernels;
+    return 0;
+}
+
+int vae21_trainer_dp_adam(vae21_trainer* t, void* stream) {
+    if (int rc = trainer_use(t)) return rc;
+    if (!t->dpB) return fail(VAE21_ERR_STATE, "vae21_trainer_dp_begin has not been called");
+    CK(cudaGraphLaunch(t->dpB, static_cast<cudaStream_t>(stream)));
+    t->launches += 2;
     return 0;
 }
 

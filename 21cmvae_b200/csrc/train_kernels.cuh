@@ -109,13 +109,15 @@ inline void sgemm(int M, int N, int K, const float* A, int lda, const float* B, 
 }
 
 // rows idx[i] (or first + i when idx == nullptr) of the resident set -> contiguous batch buffers
-// (step != nullptr: the kernel runs inside a replayed CUDA graph and takes batch number *step of the permutation `idx`)
+// (step != nullptr: the kernel runs inside a replayed CUDA graph and takes positions first .. first + batch of batch number *step of
+// the permutation `idx`, batches being `stride` positions apart: stride = batch, first = 0 on one GPU; a data-parallel rank takes
+// its share [first, first + batch) of every global batch of `stride` rows)
 __global__ void gather_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ W, const int* __restrict__ idx,
                               long long first, int batch, int nx, int ny, float* __restrict__ xb, float* __restrict__ yb, float* __restrict__ wb,
-                              const int* __restrict__ step) {
+                              const int* __restrict__ step, int stride) {
     const int row = blockIdx.x;
     if (row >= batch) return;
-    const long long src = step ? idx[static_cast<long long>(*step) * batch + row] : (idx ? idx[row] : first + row);
+    const long long src = step ? idx[static_cast<long long>(*step) * stride + first + row] : (idx ? idx[row] : first + row);
     for (int j = threadIdx.x; j < ny; j += blockDim.x) yb[static_cast<size_t>(row) * ny + j] = Y[src * ny + j];
     for (int j = threadIdx.x; j < nx; j += blockDim.x) xb[static_cast<size_t>(row) * nx + j] = X[src * nx + j];
     if (threadIdx.x == 0) wb[row] = W[src];

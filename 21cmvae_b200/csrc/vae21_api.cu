@@ -93,10 +93,7 @@ struct PinnedPool {
 PinnedPool g_pool;
 
 #ifndef VAE21_FP32_PIPE_DEFAULT
-#define VAE21_FP32_PIPE_DEFAULT 1  // barrier-free FP32 kernel (bit-identical to the block-barrier one; 17.60 -> 16.36 ms per 1M rows before de-phasing)
-#endif
-#ifndef VAE21_FP32_SKEW_DEFAULT
-#define VAE21_FP32_SKEW_DEFAULT 700  // cycles by which warps 4..7 are delayed once (see fp32_pipe_kernel.cuh)
+#define VAE21_FP32_PIPE_DEFAULT 1  // barrier-free FP32 kernel (bit-identical to the block-barrier one; 17.60 -> 15.09 ms per 1M rows)
 #endif
 constexpr int NSLOT = 3;              // pipeline depth of the host-buffer path
 constexpr long long CHUNK_ROWS = 32768;  // rows per pipeline chunk (59 MB of output)
@@ -116,7 +113,7 @@ struct vae21_handle {
     size_t f32_smem = 0;
     int f32_wst = 3;
     // barrier-free variant (fp32_pipe_kernel.cuh): rows of its single in-place activation buffer and its shared-memory bytes
-    int f32p_rows = 0;
+    int f32p_rows = 0, f32p_stages = 0;
     size_t f32p_smem = 0;
     // tensor-core path
     tck::Plan tc{};
@@ -240,6 +237,8 @@ int pack_fp32(vae21_handle* h, const float* const* kernels, const float* const* 
                     act, stage);
     h->f32_smem = act + h->f32_wst * stage;
     h->f32p_rows = std::max(m.buf_rows[0], m.buf_rows[1]);
+    h->f32p_stages = 0;
+    for (int l = 0; l < h->n_layers; ++l) h->f32p_stages += m.L[l].Kpad / f32p::KB;
     h->f32p_smem = f32p::HEADER_BYTES + static_cast<size_t>(h->f32p_rows) * f32k::LDA * sizeof(float) +
                    static_cast<size_t>(f32p::WST) * f32p::STAGE_FLOATS * sizeof(float);  // <= 224 KB for any width <= 480
     if (h->d_w32) cudaFree(h->d_w32);
@@ -261,11 +260,9 @@ int launch_fp32(vae21_handle* h, const LaunchArgs& a, cudaStream_t st) {
     const int grid = (int)std::min<long long>(ntiles, h->sm_count);
     // VAE21_FP32_PIPE=0 selects the block-barrier kernel (same bits; kept for A/B measurements and for stacks the ring does not fit)
     static const int pipe_env = std::getenv("VAE21_FP32_PIPE") ? std::atoi(std::getenv("VAE21_FP32_PIPE")) : VAE21_FP32_PIPE_DEFAULT;
-    const char* skew_s = std::getenv("VAE21_FP32_SKEW");  // read per launch (tools/fp32_ab.py sweeps it inside one process)
-    const int skew_env = skew_s ? std::atoi(skew_s) : VAE21_FP32_SKEW_DEFAULT;
-    if (pipe_env && h->f32p_smem <= 227 * 1024)
+    if (pipe_env && h->f32p_smem <= 227 * 1024 && h->f32p_stages <= f32p::MAX_STAGES)
         f32p::vae21_fp32_pipe_kernel<<<grid, f32p::NTHREADS, h->f32p_smem, st>>>(h->f32, h->nc, a, h->d_w32, h->d_b32, h->f32p_rows,
-                                                                                  skew_env);
+                                                                                  h->f32p_stages);
     else if (h->f32_wst == 3)
         f32k::vae21_fp32_kernel<3><<<grid, f32k::NTHREADS, h->f32_smem, st>>>(h->f32, h->nc, a, h->d_w32, h->d_b32);
     else

@@ -185,6 +185,10 @@ def fit(dims: Sequence[int], relu: Sequence[int], flat_params: np.ndarray, x, y,
     state = FitState(tr, optimizer)
     hist = {"loss": [], "val_loss": [], "lr": []}
     timing = {"allreduce_s": 0.0} if os.environ.get("VAE21_TRAIN_TIMING") else None
+    # experiment / test switches: VAE21_TRAIN_PER_BATCH=1 runs the data-parallel per-batch schedule on one GPU as well (no collective),
+    # VAE21_TRAIN_DP_NO_GRAPH=1 issues that schedule's kernels one by one instead of replaying the two captured graphs
+    force_per_batch = bool(os.environ.get("VAE21_TRAIN_PER_BATCH"))
+    use_graphs = not os.environ.get("VAE21_TRAIN_DP_NO_GRAPH")
     for cb in callbacks:
         cb.on_train_begin(state)
     for epoch in range(int(epochs)):
@@ -195,12 +199,36 @@ def fit(dims: Sequence[int], relu: Sequence[int], flat_params: np.ndarray, x, y,
             perm = pt.cpu().numpy()
         d_perm = torch.as_tensor(perm.astype(np.int32), device=dev)
         loss_acc.zero_()
-        if world == 1:
+        per_batch = world > 1 or force_per_batch
+        if not per_batch:
             # one GPU: the whole epoch in one library call (no Python between batches)
             tr.epoch(dx, dy, dw, d_perm, n, batch_size, optimizer.learning_rate, optimizer.beta_1, optimizer.beta_2, optimizer.epsilon,
                      optimizer.iterations, loss_acc, stream=stream)
             optimizer.iterations += (n + batch_size - 1) // batch_size
-        for lo in (range(0, n, batch_size) if world > 1 else ()):
+        n_graph = 0
+        if per_batch and use_graphs and n >= 2 * batch_size:
+            # data parallel: every FULL batch is two graph replays around the all-reduce (this rank's share of a batch is the same
+            # position range in every batch), the learning rates of the epoch's updates are precomputed on the device
+            a0, b0 = shard_batch(0, batch_size, world, rank)
+            tr.dp_begin(dx, dy, dw, d_perm, n, batch_size, a0, b0 - a0, optimizer.learning_rate, optimizer.beta_1, optimizer.beta_2,
+                        optimizer.epsilon, optimizer.iterations, grad, loss_acc, stream=stream)
+            n_graph = n // batch_size
+            for _ in range(n_graph):
+                if b0 > a0:
+                    tr.dp_forward_backward(stream=stream)
+                else:
+                    grad.zero_()
+                if distributed and world > 1:
+                    if timing is not None:
+                        torch.cuda.synchronize()
+                        t_a = time.perf_counter()
+                    dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+                    if timing is not None:
+                        torch.cuda.synchronize()
+                        timing["allreduce_s"] += time.perf_counter() - t_a
+                tr.dp_adam(stream=stream)
+            optimizer.iterations += n_graph
+        for lo in (range(n_graph * batch_size, n, batch_size) if per_batch else ()):
             hi = min(lo + batch_size, n)
             a, b = shard_batch(lo, hi, world, rank)
             if b > a:
@@ -217,7 +245,9 @@ def fit(dims: Sequence[int], relu: Sequence[int], flat_params: np.ndarray, x, y,
                     timing["allreduce_s"] += time.perf_counter() - t_a
             optimizer.iterations += 1
             t = optimizer.iterations
-            lr_t = optimizer.learning_rate * math.sqrt(1.0 - optimizer.beta_2**t) / (1.0 - optimizer.beta_1**t)
+            # (the betas reach the kernels as C floats; the library's epoch / dp_begin use those values here too)
+            b1f, b2f = float(np.float32(optimizer.beta_1)), float(np.float32(optimizer.beta_2))
+            lr_t = float(np.float32(optimizer.learning_rate)) * math.sqrt(1.0 - b2f**t) / (1.0 - b1f**t)
             tr.adam(grad, lr_t, optimizer.beta_1, optimizer.beta_2, optimizer.epsilon, stream=stream)
         if distributed and world > 1:
             dist.all_reduce(loss_acc, op=dist.ReduceOp.SUM)

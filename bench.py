@@ -405,6 +405,25 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms2 = float(t.item())
         also = {"precision_path": "bf16x3", "ms_per_step": ms2, "value": world * n / (ms2 * 1e-3), "steps": k2}
+    # ---- and the FP32-SIMT parity path (the one the tolerance of every other path is stated against), rank 0's GPU, N = 1 only
+    also_fp32 = None
+    if world == 1 and prec_name != "fp32":
+        p3 = L.PRECISIONS["fp32"]
+        for _ in range(2):
+            h.predict(d_params, out=d_out, precision=p3, stream=stream)
+        torch.cuda.synchronize()
+        k3 = 5
+        e0.record(stream)
+        for _ in range(k3):
+            h.predict(d_params, out=d_out, precision=p3, stream=stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms3 = e0.elapsed_time(e1) / k3
+        tf3 = n * FLOP_PER_SIGNAL / (ms3 * 1e-3) / 1e12
+        also_fp32 = {"precision_path": "fp32", "ms_per_step": ms3, "value": n / (ms3 * 1e-3), "steps": k3, "tflops_fp32": tf3,
+                     "frac_of_nominal_fp32_fma_peak": tf3 / 74.4,
+                     "note": "CUDA-core FFMA2 kernel (csrc/fp32_pipe_kernel.cuh); 74.4 TFLOP/s = 148 SMs x 128 lanes x 2 x 1.965 GHz; "
+                             "the kernel's own register tile tops out at 84 % of that in isolation (tools/ffma2_probe.cu)"}
 
     if rank == 0:
         pk = peaks()
@@ -468,6 +487,7 @@ def main():
             "e2e_pageable": ({"value": world * n / pg_s, "unit": UNIT,
                               "note": "plain numpy in, a fresh array out (the reference API's calling convention)"} if pg_s else None),
             "also": also,
+            "also_fp32": also_fp32,
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "check": {"max_abs_err_mK": max_mk, "max_err_over_amplitude": rel, "rows_checked": int(len(idx))},
         }

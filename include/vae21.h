@@ -224,6 +224,18 @@ int vae21_trainer_adam(vae21_trainer* t, const float* grad, float lr_t, float be
  * replay one captured CUDA graph (batch number and learning rate are read from device memory).  Bitwise identical to the calls. */
 int vae21_trainer_epoch(vae21_trainer* t, const float* x_all, const float* y_all, const float* w_all, const int* perm, int64_t n, int batch,
                         float lr, float beta1, float beta2, float eps, int64_t iterations_before, float* loss_sum, void* stream);
+/* Data-parallel epoch on one rank: the step is TWO replayable CUDA graphs around the caller's all-reduce of `grad` (NCCL lives in the
+ * host runtime, not in this library).  vae21_trainer_dp_begin copies the epoch's permutation and learning rates (update numbers
+ * iterations_before + 1 ...) to the device, resets the step counter and captures -- once per (buffers, batch, share) -- graph A:
+ * rows perm[k*batch + share_first .. + share_rows) of step k -> forward, loss (loss_sum += ...), backward into `grad` scaled by
+ * 1 / (n_out * batch), and graph B: Adam from `grad` with the step's learning rate, step counter += 1.  Per FULL batch k the caller
+ * runs: vae21_trainer_dp_forward_backward (skip it and zero `grad` when share_rows == 0), all-reduce, vae21_trainer_dp_adam.  The
+ * trailing short batch goes through vae21_trainer_forward_backward / vae21_trainer_adam.  Same arithmetic as those calls. */
+int vae21_trainer_dp_begin(vae21_trainer* t, const float* x_all, const float* y_all, const float* w_all, const int* perm, int64_t n, int batch,
+                           int share_first, int share_rows, float lr, float beta1, float beta2, float eps, int64_t iterations_before,
+                           float* grad, float* loss_sum, void* stream);
+int vae21_trainer_dp_forward_backward(vae21_trainer* t, void* stream);
+int vae21_trainer_dp_adam(vae21_trainer* t, void* stream);
 int vae21_trainer_launches(vae21_trainer* t, int64_t* n);
 
 #ifdef __cplusplus

@@ -327,3 +327,28 @@ def test_fit_continues_from_the_optimizers_saved_state(rm, tmp_path):
     # and a fresh optimiser (moments reset) does NOT reproduce it: the state matters
     cold, _ = tr.fit(dims, relu, tr.flatten_weights(w2.kernels, w2.biases), x, y, w, optimizer=tr.Adam(0.01), epochs=1, batch_size=64, shuffle=False)
     assert not np.array_equal(cold, ref)
+
+
+@pytest.mark.gpu
+def test_data_parallel_graph_schedule_equals_the_other_schedules(rm, monkeypatch):
+    """The data-parallel schedule (per batch: graph A = this rank's share forward/backward, [all-reduce], graph B = Adam) run on ONE
+    GPU, with and without graph replay, gives the bits of the single-call epoch: three routes to the same arithmetic.  (Two ranks
+    with NCCL between A and B: tests/test_multigpu_gpu.py.)"""
+    tr = pkg("training")
+    dims, n = (7, 40, 24, 451), 64 * 5 + 17
+    ks, bs, relu, x, y, mos = _problem(dims, n, 11, rm)
+    from oracle import train_ref as tref
+
+    w = tref.sample_weights(y, mos).astype(np.float32)
+    flat0 = tr.flatten_weights(ks, bs)
+    kw = dict(epochs=3, batch_size=64, seed=3, x_val=x[:50], y_val=y[:50], w_val=w[:50])
+    ref, h_ref = tr.fit(dims, relu, flat0, x, y, w, optimizer=tr.Adam(0.01), **kw)
+    monkeypatch.setenv("VAE21_TRAIN_PER_BATCH", "1")
+    graph, h_graph = tr.fit(dims, relu, flat0, x, y, w, optimizer=tr.Adam(0.01), **kw)
+    monkeypatch.setenv("VAE21_TRAIN_DP_NO_GRAPH", "1")
+    plain, h_plain = tr.fit(dims, relu, flat0, x, y, w, optimizer=tr.Adam(0.01), **kw)
+    assert np.array_equal(graph, plain), "graph replay differs from the same kernels launched one by one"
+    assert np.array_equal(graph, ref), "per-batch schedule differs from the single-call epoch"
+    assert h_graph["loss"] == h_plain["loss"] == h_ref["loss"] and h_graph["val_loss"] == h_ref["val_loss"]
+    # the graph schedule runs the same kernels (counted per replay) plus its step counter
+    assert h_graph["kernel_launches"] >= h_plain["kernel_launches"]
