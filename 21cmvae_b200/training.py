@@ -185,10 +185,12 @@ def fit(dims: Sequence[int], relu: Sequence[int], flat_params: np.ndarray, x, y,
     state = FitState(tr, optimizer)
     hist = {"loss": [], "val_loss": [], "lr": []}
     timing = {"allreduce_s": 0.0} if os.environ.get("VAE21_TRAIN_TIMING") else None
-    # experiment / test switches: VAE21_TRAIN_PER_BATCH=1 runs the data-parallel per-batch schedule on one GPU as well (no collective),
-    # VAE21_TRAIN_DP_NO_GRAPH=1 issues that schedule's kernels one by one instead of replaying the two captured graphs
+    # experiment / test switches: VAE21_TRAIN_PER_BATCH=1 runs the data-parallel per-batch schedule on one GPU as well (no collective);
+    # VAE21_TRAIN_DP_GRAPH=1 replays that schedule's step as two captured graphs around the all-reduce instead of issuing its 23
+    # kernels one by one.  Same bits; measured SLOWER on 2 x B200 (0.0372 vs 0.0277 s per epoch, profiles/r2_train_n2_*.json: the
+    # step is bound by the GPU's small-kernel latency, not by the host's launch rate), hence opt-in
     force_per_batch = bool(os.environ.get("VAE21_TRAIN_PER_BATCH"))
-    use_graphs = not os.environ.get("VAE21_TRAIN_DP_NO_GRAPH")
+    use_graphs = bool(os.environ.get("VAE21_TRAIN_DP_GRAPH"))
     for cb in callbacks:
         cb.on_train_begin(state)
     for epoch in range(int(epochs)):

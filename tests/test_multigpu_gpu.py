@@ -144,12 +144,19 @@ def _dp_worker(rank, world, port, q):
         flat = tr.flatten_weights(ks, bs)
         out, hist = tr.fit(dims, [int(r) for r in relu], flat, x, y, w, optimizer=tr.Adam(1e-3), epochs=2, batch_size=256, seed=9,
                            device=rank, distributed=True)
+        # the same run with every full batch replayed as two captured graphs around the NCCL all-reduce (opt-in schedule)
+        os.environ["VAE21_TRAIN_DP_GRAPH"] = "1"
+        try:
+            out_g, _ = tr.fit(dims, [int(r) for r in relu], flat, x, y, w, optimizer=tr.Adam(1e-3), epochs=2, batch_size=256, seed=9,
+                              device=rank, distributed=True)
+        finally:
+            del os.environ["VAE21_TRAIN_DP_GRAPH"]
         ref = None
         if rank == 0:
             ref, hist1 = tr.fit(dims, [int(r) for r in relu], flat, x, y, w, optimizer=tr.Adam(1e-3), epochs=2, batch_size=256, seed=9,
                                 device=0, distributed=False)
             ref = (ref, hist1["loss"])
-        q.put((rank, (out, hist["loss"], ref)))
+        q.put((rank, (out, hist["loss"], ref, out_g)))
     finally:
         dist.destroy_process_group()
 
@@ -157,8 +164,9 @@ def _dp_worker(rank, world, port, q):
 def test_nccl_data_parallel_training_equals_single_gpu():
     _need_two_gpus()
     res = _spawn(_dp_worker)
-    (p0, l0, ref), (p1, l1, _) = res[0], res[1]
+    (p0, l0, ref, g0), (p1, l1, _, g1) = res[0], res[1]
     assert np.array_equal(p0, p1)  # replicas stay bit-identical: same all-reduced gradient, same Adam
+    assert np.array_equal(g0, p0) and np.array_equal(g1, p1)  # graph replay around the all-reduce: the same bits
     ref_p, ref_l = ref
     scale = np.abs(ref_p).max()
     assert np.max(np.abs(p0 - ref_p)) <= 2e-4 * scale  # sharded batch sums differ from the full-batch sum only in rounding

@@ -344,9 +344,9 @@ def test_data_parallel_graph_schedule_equals_the_other_schedules(rm, monkeypatch
     kw = dict(epochs=3, batch_size=64, seed=3, x_val=x[:50], y_val=y[:50], w_val=w[:50])
     ref, h_ref = tr.fit(dims, relu, flat0, x, y, w, optimizer=tr.Adam(0.01), **kw)
     monkeypatch.setenv("VAE21_TRAIN_PER_BATCH", "1")
-    graph, h_graph = tr.fit(dims, relu, flat0, x, y, w, optimizer=tr.Adam(0.01), **kw)
-    monkeypatch.setenv("VAE21_TRAIN_DP_NO_GRAPH", "1")
     plain, h_plain = tr.fit(dims, relu, flat0, x, y, w, optimizer=tr.Adam(0.01), **kw)
+    monkeypatch.setenv("VAE21_TRAIN_DP_GRAPH", "1")
+    graph, h_graph = tr.fit(dims, relu, flat0, x, y, w, optimizer=tr.Adam(0.01), **kw)
     assert np.array_equal(graph, plain), "graph replay differs from the same kernels launched one by one"
     assert np.array_equal(graph, ref), "per-batch schedule differs from the single-call epoch"
     assert h_graph["loss"] == h_plain["loss"] == h_ref["loss"] and h_graph["val_loss"] == h_ref["val_loss"]
