@@ -26,6 +26,13 @@
 #pragma once
 #include "fp32_kernel.cuh"
 
+#ifndef VAE21_F32P_XPF
+#define VAE21_F32P_XPF 0  // 1: carry the next stage's first operands across the hand-off (software pipeline over stages)
+#endif
+#ifndef VAE21_F32P_MID
+#define VAE21_F32P_MID 0  // 1: cursor bookkeeping + next-stage probe in the middle of the unrolled body
+#endif
+
 namespace f32p {
 
 using f32k::Layer;
@@ -169,55 +176,122 @@ __device__ __forceinline__ void run_layer(const Layer& L, bool last, const float
 #pragma unroll
     for (int j = 0; j < TN; ++j) bv[j] = __ldg(Bg + L.b_off + col_of(j));
 
-    for (int kb = 0; kb < nkb; ++kb) {
-        // hand-off: ONE rarely taken branch in the common path (this warp's turn to issue comes every 8th stage; the stage's data
-        // has usually been seen by the previous stage's probe)
+    // operands of one k: the warp's 8 row values (two broadcast LDS.128) and the lane's TN weights
+    struct Ops {
+        float4 a0, a1;
+        float2 wp[NP > 0 ? NP : 1];
+        float w1;
+    };
+    auto load_ops = [&](Ops& o, const float* ak, const float* wk) {
+        o.a0 = *reinterpret_cast<const float4*>(ak);
+        o.a1 = *reinterpret_cast<const float4*>(ak + 4);
+        o.w1 = 0.f;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wk + 128 * q + 4 * lane);
+            o.wp[2 * q] = make_float2(w4.x, w4.y);
+            o.wp[2 * q + 1] = make_float2(w4.z, w4.w);
+        }
+        if (NS >= 2) o.wp[NP > 0 ? NP - 1 : 0] = *reinterpret_cast<const float2*>(wk + 128 * NQ + 2 * lane);
+        if (ODD) o.w1 = wk[128 * NQ + (NS >= 2 ? 64 : 0) + lane];
+    };
+    auto fma_ops = [&](const Ops& o) {
+        const float av[8] = {o.a0.x, o.a0.y, o.a0.z, o.a0.w, o.a1.x, o.a1.y, o.a1.z, o.a1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 aa = make_float2(av[i], av[i]);
+#pragma unroll
+            for (int q = 0; q < NP; ++q) acc2[i][q] = __ffma2_rn(aa, o.wp[q], acc2[i][q]);
+            if (ODD) acc1[i] = fmaf(av[i], o.w1, acc1[i]);
+        }
+    };
+    // hand-off into the stage at the consumer position (p.cs / p.cph / p.g): ONE rarely taken branch in the common path (this
+    // warp's turn to issue comes every 8th stage; the stage's data has usually been seen by the previous stage's probe)
+    auto acquire = [&]() {
         const bool mine = static_cast<int>(p.g & (NWARPS - 1)) == warp && p.pt > 0;
         if (mine || !p.ready) {
             if (mine) issue_stage(p, lane == 0);
             if (!p.ready) mbar_wait(p.full0 + 8u * p.cs, p.cph);
         }
+    };
+    // cursor bookkeeping + non-blocking probe of the NEXT stage's barrier: its answer travels under this stage's FMAs, so that the
+    // usual hand-off costs no barrier round trip
+    auto look_ahead = [&]() {
         advance_cursor(p);
-        {   // probe the NEXT stage's barrier now (non-blocking): its answer travels under this stage's FMAs, so that the usual
-            // hand-off costs no barrier round trip
-            const uint32_t ns = p.cs + 1 == static_cast<uint32_t>(WST) ? 0u : p.cs + 1;
-            p.ready = mbar_test(p.full0 + 8u * ns, ns ? p.cph : p.cph ^ 1u);
+        const uint32_t ns = p.cs + 1 == static_cast<uint32_t>(WST) ? 0u : p.cs + 1;
+        p.ready = mbar_test(p.full0 + 8u * ns, ns ? p.cph : p.cph ^ 1u);
+    };
+    auto release = [&]() {
+        __syncwarp();  // (also orders every lane's reads of `act` before the in-place stores of the epilogue)
+        if (lane == 0) mbar_arrive(p.empty0 + 8u * p.cs);  // every lane's reads of the slot have returned: release it
+        const bool wrap = p.cs + 1 == static_cast<uint32_t>(WST);
+        p.cs = wrap ? 0u : p.cs + 1;
+        p.cph ^= wrap ? 1u : 0u;
+        ++p.g;
+    };
+
+#if VAE21_F32P_XPF
+    // software pipeline ACROSS the hand-off: the operands of the next stage's first k are loaded (after that stage has been
+    // acquired) before the FMAs of this stage's last k, so no stage opens with an exposed shared-memory round trip
+    Ops cur, nxt;
+    acquire();
+    look_ahead();
+    load_ops(cur, act + 8 * warp, p.ring + p.cs * STAGE_FLOATS);
+    for (int kb = 0; kb < nkb; ++kb) {
+        const float* ws = p.ring + p.cs * STAGE_FLOATS;
+        const float* ap = act + (kb * KBL) * LDA + 8 * warp;
+        const bool more = kb + 1 < nkb;
+#pragma unroll
+        for (int kk = 0; kk < KBL; ++kk) {
+            if (kk + 1 < KBL) {
+                load_ops(nxt, ap + (kk + 1) * LDA, ws + (kk + 1) * Npad);
+                fma_ops(cur);
+            } else {
+                // this stage's slot stays held (its last operands are in `cur`, read already) while the next one is acquired
+                const uint32_t held = p.cs, held_ph = p.cph;
+                if (more) {
+                    const bool wrap = p.cs + 1 == static_cast<uint32_t>(WST);
+                    p.cs = wrap ? 0u : p.cs + 1;
+                    p.cph ^= wrap ? 1u : 0u;
+                    ++p.g;
+                    acquire();
+                    look_ahead();
+                    load_ops(nxt, ap + KBL * LDA, p.ring + p.cs * STAGE_FLOATS);
+                }
+                fma_ops(cur);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p.empty0 + 8u * held);
+                (void)held_ph;
+                if (!more) {  // leave the consumer position at the first stage of the next layer
+                    const bool wrap = p.cs + 1 == static_cast<uint32_t>(WST);
+                    p.cs = wrap ? 0u : p.cs + 1;
+                    p.cph ^= wrap ? 1u : 0u;
+                    ++p.g;
+                }
+            }
+            cur = nxt;
         }
+    }
+#else
+    for (int kb = 0; kb < nkb; ++kb) {
+        acquire();
+#if !VAE21_F32P_MID
+        look_ahead();
+#endif
         const float* ws = p.ring + p.cs * STAGE_FLOATS;
         const float* ap = act + (kb * KBL) * LDA + 8 * warp;
 #pragma unroll
         for (int kk = 0; kk < KBL; ++kk) {
-            const float4 a0 = *reinterpret_cast<const float4*>(ap + kk * LDA);
-            const float4 a1 = *reinterpret_cast<const float4*>(ap + kk * LDA + 4);
-            const float* wk = ws + kk * Npad;
-            float2 wp[NP > 0 ? NP : 1];
-            float w1 = 0.f;
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                const float4 w4 = *reinterpret_cast<const float4*>(wk + 128 * q + 4 * lane);
-                wp[2 * q] = make_float2(w4.x, w4.y);
-                wp[2 * q + 1] = make_float2(w4.z, w4.w);
-            }
-            if (NS >= 2) wp[NP > 0 ? NP - 1 : 0] = *reinterpret_cast<const float2*>(wk + 128 * NQ + 2 * lane);
-            if (ODD) w1 = wk[128 * NQ + (NS >= 2 ? 64 : 0) + lane];
-            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float2 aa = make_float2(av[i], av[i]);
-#pragma unroll
-                for (int q = 0; q < NP; ++q) acc2[i][q] = __ffma2_rn(aa, wp[q], acc2[i][q]);
-                if (ODD) acc1[i] = fmaf(av[i], w1, acc1[i]);
-            }
+#if VAE21_F32P_MID
+            if (kk == KBL / 2) look_ahead();  // the bookkeeping sits between FMAs instead of ahead of the stage's first loads
+#endif
+            Ops o;
+            load_ops(o, ap + kk * LDA, ws + kk * Npad);
+            fma_ops(o);
         }
-        __syncwarp();  // (also orders every lane's reads of `act` before the in-place stores of the epilogue)
-        if (lane == 0) mbar_arrive(p.empty0 + 8u * p.cs);  // every lane's reads of the slot have returned: release it
-        {
-            const bool wrap = p.cs + 1 == static_cast<uint32_t>(WST);
-            p.cs = wrap ? 0u : p.cs + 1;
-            p.cph ^= wrap ? 1u : 0u;
-        }
-        ++p.g;
+        release();
     }
+#endif
 
     float acc[8][TN];  // register renaming only: slot j of the epilogues below is column col_of(j)
 #pragma unroll

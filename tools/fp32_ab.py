@@ -1,6 +1,8 @@
 """A/B of the two FP32 kernels (block-barrier `f32k` vs barrier-free `f32p`, csrc/fp32_pipe_kernel.cuh): the outputs must be
 BIT-IDENTICAL (same products, same k order), only the time may differ.
-    python tools/fp32_ab.py            # runs itself twice (VAE21_FP32_PIPE=0 / 1), compares every saved array, prints one JSON line
+    python tools/fp32_ab.py [name=path/to/libvae21_variant.so ...]
+runs itself once per kernel (VAE21_FP32_PIPE=0 / 1, plus one child per extra library given as name=path: builds of the pipe
+kernel with other compile-time switches, loaded through VAE21_LIB), compares every saved array, prints one JSON line.
 The child mode (`--child TAG`) evaluates, for the DirectEmulator stack and the reference's trained AE chain: predict on ragged
 row counts (f64 and f32 parameters), fused chi^2 + argmin, the fused error, a device-generated grid, and times 1M-row launches.
 """
@@ -78,19 +80,27 @@ def main():
         return
     outdir = tempfile.mkdtemp(prefix="fp32_ab_")
     lines = {}
-    for tag, val in (("barrier", "0"), ("pipe", "1")):
+    runs = [("barrier", "0", None), ("pipe", "1", None)]
+    for spec in sys.argv[1:]:
+        name, path = spec.split("=", 1)
+        runs.append((name, "1", os.path.abspath(path)))
+    for tag, val, lib in runs:
         env = dict(os.environ, VAE21_FP32_PIPE=val)
+        if lib:
+            env["VAE21_LIB"] = lib
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", tag, outdir], env=env, capture_output=True,
                            text=True, timeout=600)
         if r.returncode != 0:
             print(json.dumps({"tag": tag, "failed": r.returncode, "stderr": r.stderr[-2000:]}))
             sys.exit(1)
         lines[tag] = json.loads(r.stdout.strip().splitlines()[-1])
-    a, b = np.load(os.path.join(outdir, "barrier.npz")), np.load(os.path.join(outdir, "pipe.npz"))
-    differing = [k for k in a.files if not np.array_equal(a[k].view(np.uint8) if a[k].dtype.kind == "f" else a[k],
-                                                          b[k].view(np.uint8) if b[k].dtype.kind == "f" else b[k])]
-    print(json.dumps({"barrier": lines["barrier"], "pipe": lines["pipe"], "arrays": len(a.files), "differing": differing,
-                      "bit_identical": not differing}))
+    a = np.load(os.path.join(outdir, "barrier.npz"))
+    differing = []
+    for tag, _, _ in runs[1:]:
+        b = np.load(os.path.join(outdir, f"{tag}.npz"))
+        differing += [f"{tag}:{k}" for k in a.files if not np.array_equal(a[k].view(np.uint8) if a[k].dtype.kind == "f" else a[k],
+                                                                          b[k].view(np.uint8) if b[k].dtype.kind == "f" else b[k])]
+    print(json.dumps({**lines, "arrays": len(a.files), "differing": differing, "bit_identical": not differing}))
     sys.exit(1 if differing else 0)
 
 
