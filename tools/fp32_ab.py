@@ -4,7 +4,7 @@ BIT-IDENTICAL (same products, same k order), only the time may differ.
 runs itself once per kernel (VAE21_FP32_PIPE=0 / 1, plus one child per extra library given as name=path: builds of the pipe
 kernel with other compile-time switches, loaded through VAE21_LIB), compares every saved array, prints one JSON line.
 The child mode (`--child TAG`) evaluates, for the DirectEmulator stack and the reference's trained AE chain: predict on ragged
-row counts (f64 and f32 parameters), fused chi^2 + argmin, the fused error, a device-generated grid, and times 1M-row launches.
+row counts (f64 and f32 parameters), fused chi^2 + argmin, the fused error, and times 1M-row launches.
 """
 import importlib
 import json
