@@ -116,6 +116,77 @@ def dense_chain(x: np.ndarray, kernels: Sequence[np.ndarray], biases: Sequence[n
     return h
 
 
+FP32_ORDERS = {
+    # name: (k order, fused multiply-add, k block (0 = none), bias as the accumulator's start value)
+    "seq_fma": ("seq", True, 0, False),        # k ascending, one rounding per term: the order of this repository's FP32 kernel
+    "seq_mul_add": ("seq", False, 0, False),   # product and sum rounded separately (no FMA contraction)
+    "rev_fma": ("rev", True, 0, False),
+    "perm_fma": ("perm", True, 0, False),      # a random order of k, drawn per layer from `seed`
+    "kc128_fma": ("seq", True, 128, False),    # a GEBP-style k panel: panels summed from zero, then added to the output
+    "kc32_mul_add": ("seq", False, 32, False),
+    "bias_first_fma": ("seq", True, 0, True),  # fused MatMul+BiasAdd: the bias seeds the accumulator
+    "tree": ("tree", False, 0, False),         # pairwise summation of the separately rounded products
+}
+
+
+def dense_chain_fp32_ordered(x, kernels, biases, relu, order: str = "seq_fma", seed: int = 0) -> np.ndarray:
+    """The Dense chain of emulator.py:37-47 / :402 in float32 with an EXPLICIT summation order.
+
+    The reference hands ``h @ kernel + bias`` to TensorFlow's CPU MatMul (Eigen or oneDNN SGEMM), whose accumulation order, k
+    blocking and use of FMA are not specified and differ between builds and machines; TensorFlow is absent here.  This function
+    spans the orders such a kernel can take (``FP32_ORDERS``), so that tests can bound how far ANY float32 evaluation of the chain
+    -- TensorFlow's included -- lies from the float64 arbiter.  An fp32 FMA is emulated as float32(float64(acc) + a*w): the product
+    of two float32 is exact in float64, the sum is rounded to 53 and then to 24 bits (differs from a true FMA only in rare
+    double-rounding cases, by one ulp).
+    """
+    kind, fma, kc, bias_first = FP32_ORDERS[order]
+    rng = np.random.default_rng(seed)
+    h = np.asarray(x, dtype=np.float32)
+    if h.ndim == 1:
+        h = h[None, :]
+
+    def accumulate(h32, W32, ids, acc):
+        if fma:
+            h64, W64 = h32.astype(np.float64), W32.astype(np.float64)
+            for k in ids:
+                acc = (acc.astype(np.float64) + h64[:, k:k + 1] * W64[k:k + 1, :]).astype(np.float32)
+        else:
+            for k in ids:
+                acc = acc + h32[:, k:k + 1] * W32[k:k + 1, :]
+        return acc
+
+    for W, b, r in zip(kernels, biases, relu):
+        W = np.asarray(W, np.float32)
+        b = np.asarray(b, np.float32)
+        K, N = W.shape
+        ids = np.arange(K)
+        if kind == "rev":
+            ids = ids[::-1]
+        elif kind == "perm":
+            ids = rng.permutation(K)
+        zero = np.zeros((h.shape[0], N), np.float32)
+        if kind == "tree":
+            parts = [h[:, k:k + 1] * W[k:k + 1, :] for k in ids]
+            while len(parts) > 1:
+                nxt = [parts[i] + parts[i + 1] for i in range(0, len(parts) - 1, 2)]
+                if len(parts) % 2:
+                    nxt.append(parts[-1])
+                parts = nxt
+            out = parts[0] + b
+        else:
+            out = np.broadcast_to(b, zero.shape).astype(np.float32) if bias_first else zero
+            if kc:
+                for s in range(0, K, kc):
+                    out = out + accumulate(h, W, ids[s:s + kc], zero)
+            else:
+                out = accumulate(h, W, ids, out)
+            if not bias_first:
+                out = out + b
+        h = np.maximum(out, np.float32(0)) if r else out
+        assert h.dtype == np.float32
+    return h
+
+
 def predict(params, kernels, biases, relu, pmin, pmax, mu, sd, dtype=np.float64, squeeze=True):
     """DirectEmulator.predict restated: emulator.py:383-407.
 

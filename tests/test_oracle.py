@@ -112,3 +112,35 @@ def test_trained_fixture_is_trained_scale_and_emulates_its_teacher(rm, ae_golden
     pred = rm.predict(f["par_test"], f["kernels"], f["biases"], f["relu"], f["pmin"], f["pmax"], f["mu"], f["sd"])
     err = np.sqrt(np.mean((pred - f["signal_test"]) ** 2, axis=1)) / np.max(np.abs(f["signal_test"]), axis=1) * 100
     assert err.mean() < 1.5 and np.median(err) < 1.2, (err.mean(), np.median(err))
+
+
+def test_any_fp32_summation_order_stays_inside_the_fp32_budget(rm, trained_fixture, ae_golden):
+    """The tolerance of the FP32 path is stated against TensorFlow's CPU predict (emulator.py:402), whose SGEMM summation order is
+    unspecified and which is absent from this image.  Bound what that freedom is worth: evaluate the chain in float32 under every
+    order an SGEMM can plausibly take (sequential / reversed / permuted k, k panels, with and without FMA, bias first, pairwise) on
+    trained-scale weights.  Each lies within 2e-6 of the per-signal amplitude of the float64 arbiter and within 3e-6 of every
+    other, so |GPU FP32 path - TensorFlow| <= |GPU - float64| (measured 7e-7 on this fixture, tests/test_gpu_parity.py) + 2e-6, a fifth
+    of the 1e-5 tolerance, whichever order TensorFlow's build uses."""
+    f = trained_fixture
+    p = rm.draw_params(192, seed=11)
+    x32 = rm.par_transform_cached(p, f["pmin"], f["pmax"]).astype(np.float32)
+    y64 = rm.predict(p, f["kernels"], f["biases"], f["relu"], f["pmin"], f["pmax"], f["mu"], f["sd"], squeeze=False)
+    amp = np.max(np.abs(y64), axis=1, keepdims=True)
+    outs = {}
+    for order in rm.FP32_ORDERS:
+        y = rm.dense_chain_fp32_ordered(x32, f["kernels"], f["biases"], f["relu"], order=order, seed=5)
+        outs[order] = rm.unpreproc_cached(y, np.asarray(f["mu"], np.float32), np.float32(f["sd"]))
+        assert outs[order].dtype == np.float32
+        assert np.max(np.abs(outs[order] - y64) / amp) < 2e-6, order
+    names = list(outs)
+    spread = max(np.max(np.abs(outs[a] - outs[b]) / amp) for a in names for b in names)
+    assert 0 < spread < 3e-6, spread           # the orders DO differ (the emulation is not vacuous) and differ by little
+    # the library SGEMM of this machine is one more member of the family
+    blas = rm.predict(p, f["kernels"], f["biases"], f["relu"], f["pmin"], f["pmax"], f["mu"], f["sd"], dtype=np.float32, squeeze=False)
+    assert np.max(np.abs(blas - y64) / amp) < 2e-6
+    # same on the reference's REAL trained weights (the 8-layer AE chain, in sigma units of its output)
+    g = ae_golden
+    amp_g = np.max(np.abs(g["y64"]), axis=1, keepdims=True)
+    for order in ("seq_fma", "perm_fma", "kc32_mul_add", "tree"):
+        y = rm.dense_chain_fp32_ordered(g["x"], g["kernels"], g["biases"], g["relu"], order=order, seed=7)
+        assert np.max(np.abs(y - g["y64"]) / amp_g) < 5e-6, order
