@@ -179,7 +179,66 @@ def _unwrap(obj, want_write=False) -> Tuple[int, bool, Tuple[int, ...], np.dtype
         if np_dt is None:
             raise TypeError(f"unsupported tensor dtype {t.dtype}")
         return t.data_ptr(), t.is_cuda, tuple(t.shape), np.dtype(np_dt), (t.device.index if t.is_cuda else None), t
+    if hasattr(obj, "__dlpack__"):  # any other DLPack producer (jax, cupy without the CUDA array interface, numpy-likes, ...)
+        return _unwrap_dlpack(obj, want_write)
     raise TypeError(f"unsupported buffer type {type(obj)!r}")
+
+
+# ---- DLPack (https://dmlc.github.io/dlpack: struct DLManagedTensor, capsule name "dltensor") -------------------------------
+
+
+class _DLDevice(C.Structure):
+    _fields_ = [("device_type", C.c_int32), ("device_id", C.c_int32)]
+
+
+class _DLDataType(C.Structure):
+    _fields_ = [("code", C.c_uint8), ("bits", C.c_uint8), ("lanes", C.c_uint16)]
+
+
+class _DLTensor(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("device", _DLDevice), ("ndim", C.c_int32), ("dtype", _DLDataType),
+                ("shape", C.POINTER(C.c_int64)), ("strides", C.POINTER(C.c_int64)), ("byte_offset", C.c_uint64)]
+
+
+class _DLManagedTensor(C.Structure):
+    _fields_ = [("dl_tensor", _DLTensor), ("manager_ctx", C.c_void_p), ("deleter", C.c_void_p)]
+
+
+_DL_CPU, _DL_CUDA, _DL_CUDA_HOST, _DL_CUDA_MANAGED = 1, 2, 3, 13
+_DL_FLOAT = 2
+
+
+def _unwrap_dlpack(obj, want_write=False, stream=None):
+    """Read pointer, shape and dtype out of the DLPack capsule of `obj`.  The capsule is NOT consumed (not renamed): it is
+    returned as the keep-alive object and its own destructor releases the producer's tensor when the call is over.  A CUDA
+    producer is asked to make the data visible to `stream` (default: the legacy default stream, which is what the library
+    orders against when no stream is given)."""
+    dev_type, dev_id = (obj.__dlpack_device__() if hasattr(obj, "__dlpack_device__") else (_DL_CPU, 0))
+    dev_type = int(dev_type)
+    if dev_type in (_DL_CUDA, _DL_CUDA_MANAGED):
+        cap = obj.__dlpack__(stream=1 if stream in (None, 0) else int(stream))
+    else:
+        cap = obj.__dlpack__()
+    api = C.pythonapi
+    api.PyCapsule_IsValid.argtypes, api.PyCapsule_IsValid.restype = [C.py_object, C.c_char_p], C.c_int
+    api.PyCapsule_GetPointer.argtypes, api.PyCapsule_GetPointer.restype = [C.py_object, C.c_char_p], C.c_void_p
+    if not api.PyCapsule_IsValid(cap, b"dltensor"):
+        raise TypeError(f"{type(obj)!r}.__dlpack__() did not return an unconsumed 'dltensor' capsule")
+    t = C.cast(api.PyCapsule_GetPointer(cap, b"dltensor"), C.POINTER(_DLManagedTensor)).contents.dl_tensor
+    if t.device.device_type not in (_DL_CPU, _DL_CUDA, _DL_CUDA_HOST, _DL_CUDA_MANAGED):
+        raise TypeError(f"DLPack device type {t.device.device_type} unsupported (CPU, CUDA, pinned or managed memory)")
+    if t.dtype.code != _DL_FLOAT or t.dtype.lanes != 1 or t.dtype.bits not in (32, 64):
+        raise TypeError(f"DLPack dtype (code {t.dtype.code}, {t.dtype.bits} bits, {t.dtype.lanes} lanes) unsupported (float32/float64)")
+    shape = tuple(int(t.shape[i]) for i in range(t.ndim))
+    if t.strides:  # in ELEMENTS; NULL = compact row-major
+        acc = 1
+        for i in reversed(range(t.ndim)):
+            if shape[i] != 1 and int(t.strides[i]) != acc:
+                raise ValueError("DLPack tensor must be C-contiguous")
+            acc *= shape[i]
+    on_dev = t.device.device_type in (_DL_CUDA, _DL_CUDA_MANAGED)
+    ptr = int(t.data or 0) + int(t.byte_offset)
+    return ptr, on_dev, shape, np.dtype(np.float32 if t.dtype.bits == 32 else np.float64), (int(t.device.device_id) if on_dev else None), cap
 
 
 class Handle:

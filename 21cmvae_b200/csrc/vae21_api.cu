@@ -704,12 +704,12 @@ int vae21_error(vae21_handle* h, const void* params, int params_dtype, int param
     a.chi2 = err;
     if (!params_on_device) {
         if (cudaMalloc(&d_par, n * K0 * in_elt) != cudaSuccess) { cleanup(); return fail(VAE21_ERR_NOMEM, "device allocation failed"); }
-        cudaMemcpyAsync(d_par, params, n * K0 * in_elt, cudaMemcpyHostToDevice, st);
+        if (cudaMemcpyAsync(d_par, params, n * K0 * in_elt, cudaMemcpyHostToDevice, st) != cudaSuccess) { cleanup(); return fail(VAE21_ERR_CUDA, "parameter upload failed: %s", cudaGetErrorString(cudaGetLastError())); }
         a.in = d_par;
     }
     if (!truth_on_device) {
         if (cudaMalloc(&d_truth, sizeof(float) * n * NO) != cudaSuccess) { cleanup(); return fail(VAE21_ERR_NOMEM, "device allocation failed"); }
-        cudaMemcpyAsync(d_truth, truth, sizeof(float) * n * NO, cudaMemcpyHostToDevice, st);
+        if (cudaMemcpyAsync(d_truth, truth, sizeof(float) * n * NO, cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaStreamSynchronize(st); cleanup(); return fail(VAE21_ERR_CUDA, "upload of the true signals failed: %s", cudaGetErrorString(cudaGetLastError())); }
         a.truth = static_cast<const float*>(d_truth);
     }
     if (!err_on_device) {

@@ -373,6 +373,11 @@ class DirectEmulator:
     def _as_param_array(params):
         if _is_device_array(params):
             return params
+        if not isinstance(params, np.ndarray) and hasattr(params, "__dlpack__") and hasattr(params, "__dlpack_device__"):
+            if int(params.__dlpack_device__()[0]) in (2, 13):  # kDLCUDA / kDLCUDAManaged: handed to the library as it is
+                return params
+            if not hasattr(params, "__array__"):
+                params = np.from_dlpack(params)
         p = np.asarray(params)
         if p.ndim == 1:
             p = p[None, :]

@@ -289,3 +289,39 @@ def test_load_model_restores_the_compiled_optimizer(tmp_path, rm):
     got = e2.emulator._compiled["optimizer"]
     assert isinstance(got, tr.Adam) and got.iterations == 77 and got.learning_rate == float(np.float32(0.005))
     assert np.array_equal(got.m, opt.m) and np.array_equal(got.v, opt.v)
+
+
+class _OnlyDLPack:
+    """A buffer that speaks nothing but the DLPack protocol (what a jax array or another framework's tensor looks like)."""
+
+    def __init__(self, a):
+        self._a = a
+
+    def __dlpack__(self, stream=None):
+        return self._a.__dlpack__()
+
+    def __dlpack_device__(self):
+        return self._a.__dlpack_device__()
+
+
+def test_dlpack_buffers_are_unwrapped_without_a_copy():
+    """north_star: 'numpy/DLPack buffers'.  The binding reads pointer / shape / dtype straight out of the DLPack capsule."""
+    L = pkg("_lib")
+    a = np.arange(21, dtype=np.float64).reshape(3, 7)
+    ptr, on_dev, shape, dt, dev, keep = L._unwrap(_OnlyDLPack(a))
+    assert (ptr, on_dev, shape, dt, dev) == (a.ctypes.data, False, (3, 7), np.dtype(np.float64), None) and keep is not None
+    import torch
+
+    t = torch.arange(12, dtype=torch.float32).reshape(3, 4)[1:]       # non-zero storage offset
+    ptr, on_dev, shape, dt, _, _ = L._unwrap(_OnlyDLPack(t))
+    assert (ptr, on_dev, shape, dt) == (t.data_ptr(), False, (2, 4), np.dtype(np.float32))
+    with pytest.raises(ValueError, match="C-contiguous"):
+        L._unwrap(_OnlyDLPack(a[:, ::2]))
+    with pytest.raises(TypeError, match="float32/float64"):
+        L._unwrap(_OnlyDLPack(np.arange(6).reshape(2, 3)))
+    with pytest.raises(TypeError):
+        L._unwrap(object())
+    # the emulator front end hands a host DLPack producer to numpy without copying it
+    emu = pkg("emulator")
+    p = emu.DirectEmulator._as_param_array(_OnlyDLPack(a))
+    assert isinstance(p, np.ndarray) and p.ctypes.data == a.ctypes.data and p.shape == (3, 7)
