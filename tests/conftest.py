@@ -64,3 +64,50 @@ def have_gpu():
         return pkg("_lib").device_count() > 0
     except Exception:  # noqa: BLE001
         return False
+
+
+_C_CHAIN_SRC = os.path.join(ROOT, "oracle", "chain_fp32.c")
+_C_CHAIN_LIB = os.path.join(ROOT, "oracle", "_build", "libchain_fp32.so")
+
+
+def build_c_oracle():
+    """Compile oracle/chain_fp32.c (plain C, gcc) into oracle/_build/ unless an up-to-date library is there; None without gcc."""
+    import shutil
+    import subprocess
+
+    if os.path.isfile(_C_CHAIN_LIB) and os.path.getmtime(_C_CHAIN_LIB) >= os.path.getmtime(_C_CHAIN_SRC):
+        return _C_CHAIN_LIB
+    gcc = shutil.which("gcc") or shutil.which("cc")
+    if gcc is None:
+        return None
+    os.makedirs(os.path.dirname(_C_CHAIN_LIB), exist_ok=True)
+    subprocess.run([gcc, "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", _C_CHAIN_LIB, _C_CHAIN_SRC, "-lm"], check=True)
+    return _C_CHAIN_LIB
+
+
+@pytest.fixture(scope="session")
+def c_chain():
+    """The plain-C float32 chain (k ascending, true fmaf, bias added afterwards): `f(x, kernels, biases, relu) -> (n, out) float32`."""
+    import ctypes as C
+
+    path = build_c_oracle()
+    if path is None:
+        pytest.skip("no C compiler for oracle/chain_fp32.c")
+    lib = C.CDLL(path)
+    lib.oracle_chain_fp32_seq_fma.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oracle_chain_fp32_seq_fma.restype = C.c_int
+
+    def run(x, kernels, biases, relu):
+        x = np.ascontiguousarray(x, np.float32)
+        ks = [np.ascontiguousarray(k, np.float32) for k in kernels]
+        bs = [np.ascontiguousarray(b, np.float32) for b in biases]
+        n_l = len(ks)
+        dims = (C.c_int * (n_l + 1))(*([ks[0].shape[0]] + [k.shape[1] for k in ks]))
+        kp = (C.c_void_p * n_l)(*[k.ctypes.data for k in ks])
+        bp = (C.c_void_p * n_l)(*[b.ctypes.data for b in bs])
+        rl = (C.c_int * n_l)(*[int(bool(r)) for r in relu])
+        out = np.empty((len(x), ks[-1].shape[1]), np.float32)
+        assert lib.oracle_chain_fp32_seq_fma(x.ctypes.data, len(x), n_l, dims, kp, bp, rl, out.ctypes.data) == 0
+        return out
+
+    return run

@@ -144,3 +144,26 @@ def test_any_fp32_summation_order_stays_inside_the_fp32_budget(rm, trained_fixtu
     for order in ("seq_fma", "perm_fma", "kc32_mul_add", "tree"):
         y = rm.dense_chain_fp32_ordered(g["x"], g["kernels"], g["biases"], g["relu"], order=order, seed=7)
         assert np.max(np.abs(y - g["y64"]) / amp_g) < 5e-6, order
+
+
+def test_c_chain_is_a_third_implementation_and_validates_the_fma_emulation(rm, c_chain, trained_fixture, ae_golden):
+    """oracle/chain_fp32.c: the chain in plain C with true fmaf, k ascending -- the arithmetic order of the FP32 CUDA kernel.
+    (1) It agrees with the float64 arbiter to float32 accuracy on both sets of trained weights; (2) the numpy emulation of an
+    fp32 FMA through float64 (`dense_chain_fp32_ordered(order="seq_fma")`) reproduces it bit for bit, so the summation-order
+    envelope above is an envelope of REAL fused multiply-adds."""
+    f = trained_fixture
+    x32 = rm.par_transform_cached(rm.draw_params(192, seed=11), f["pmin"], f["pmax"]).astype(np.float32)
+    yc = c_chain(x32, f["kernels"], f["biases"], f["relu"])
+    y64 = rm.dense_chain(x32, f["kernels"], f["biases"], f["relu"])
+    assert np.max(np.abs(yc - y64)) / np.max(np.abs(y64)) < 2e-6
+    yn = rm.dense_chain_fp32_ordered(x32, f["kernels"], f["biases"], f["relu"], order="seq_fma")
+    assert np.array_equal(yc, yn)
+    g = ae_golden
+    yc = c_chain(g["x"], g["kernels"], g["biases"], g["relu"])
+    assert np.max(np.abs(yc - g["y64"]) / np.max(np.abs(g["y64"]), axis=1, keepdims=True)) < 5e-6
+    assert np.array_equal(yc, rm.dense_chain_fp32_ordered(g["x"], g["kernels"], g["biases"], g["relu"], order="seq_fma"))
+    # NaN propagates through ReLU like tf.nn.relu (and like the CUDA kernels)
+    bad = x32[:2].copy()
+    bad[0, 0] = np.nan
+    out = c_chain(bad, f["kernels"], f["biases"], f["relu"])
+    assert np.all(np.isnan(out[0])) and not np.any(np.isnan(out[1]))
