@@ -35,6 +35,21 @@ def test_no_cpu_fallback_without_gpu():
         e.predict(np.ones(7))
 
 
+def test_the_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing the package ships (Python, CUDA/C++ sources, the import shim, the header) may
+    import, include, load or even name it -- only tests/, bench.py's CPU legs and __graft_entry__ (build + smoke check) do."""
+    shipped = []
+    for top in ("21cmvae_b200", "VeryAccurateEmulator", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            shipped += [os.path.join(dirpath, f) for f in files if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp"))]
+    assert len(shipped) > 15
+    pat = re.compile(r"\boracle\b|refmath|train_ref|mcmc_ref|chain_fp32")
+    for path in shipped:
+        hits = [ln.strip() for ln in open(path, encoding="utf-8", errors="replace") if pat.search(ln)]
+        # the only mentions allowed are comments/docstrings saying that a CPU oracle EXISTS for a kernel
+        assert not [h for h in hits if re.search(r"\b(import|include|CDLL|dlopen|open)\b", h)], (path, hits)
+
+
 def test_null_and_state_errors_are_reported_not_crashes():
     L = pkg("_lib")
     lib = L.load()
