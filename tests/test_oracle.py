@@ -167,3 +167,30 @@ def test_c_chain_is_a_third_implementation_and_validates_the_fma_emulation(rm, c
     bad[0, 0] = np.nan
     out = c_chain(bad, f["kernels"], f["biases"], f["relu"])
     assert np.all(np.isnan(out[0])) and not np.any(np.isnan(out[1]))
+
+
+def test_simulated_operand_formats_meet_the_budget_on_trained_weights(ae_golden, trained_fixture):
+    """The arithmetic of the three tensor-core operand formats restated in float64 numpy (tools/precision_study.py: exact products
+    of the rounded operands; bf16 / fp16 hi-lo splits; fp16 + e4m3 first-order corrections at accumulator scale 2^11), on the
+    reference's real trained chain and on the trained DirectEmulator fixture.  CPU-checkable form of the claim the GPU tests make
+    on the real kernels (tests/test_gpu_parity.py): every split format sits inside 0.01 mK rms / 0.05 mK max with margin, and
+    one-pass 16-bit operands do NOT -- which is why the kernel spends 2-3 tensor passes per k-step."""
+    import importlib.util
+
+    from conftest import ROOT
+
+    spec = importlib.util.spec_from_file_location("precision_study", os.path.join(ROOT, "tools", "precision_study.py"))
+    ps = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ps)
+    g, f = ae_golden, trained_fixture
+    for name, ks, bs, relu, sigma_mk in (("ae_chain", g["kernels"], g["biases"], g["relu"], 50.0),
+                                         ("direct_trained", f["kernels"], f["biases"], f["relu"], float(f["sd"]))):
+        rows, _ = ps.study(name, ks, bs, relu, 2000, sigma_mk)
+        by = {r["format"]: r for r in rows}
+        for fmt, margin in (("bf16x3", 4.0), ("fp16x3", 50.0), ("fp16e4m3", 2.5)):
+            assert by[fmt]["rms_max_mK"] * margin <= 0.01 and by[fmt]["max_abs_mK"] * margin <= 0.05, (name, by[fmt])
+        assert not by["bf16x1"]["inside_budget"] and not by["fp16x1"]["inside_budget"], name
+        assert by["fp32"]["max_over_amplitude"] < 1e-5
+    # the e4m3 rounding used by the simulation: exact on representable values, ties to even, saturating at 448
+    v = np.array([0.0, 2.0 ** -9, 0.0625, 1.0, 1.125, 1.0625, 1.1875, 448.0, 1000.0, -3.3])
+    assert np.array_equal(ps.rn_e4m3(v), np.array([0.0, 2.0 ** -9, 0.0625, 1.0, 1.125, 1.0, 1.25, 448.0, 448.0, -3.25]))
