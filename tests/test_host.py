@@ -340,3 +340,64 @@ def test_dlpack_buffers_are_unwrapped_without_a_copy():
     emu = pkg("emulator")
     p = emu.DirectEmulator._as_param_array(_OnlyDLPack(a))
     assert isinstance(p, np.ndarray) and p.ctypes.data == a.ctypes.data and p.shape == (3, 7)
+
+
+def test_the_h5py_branch_of_the_loader_on_an_h5py_shaped_file_object(monkeypatch, trained_fixture, tmp_path):
+    """north_star: weights are read 'via h5py'.  h5py is absent from this image (the built-in reader serves instead), so the
+    branch that calls it is driven here with a stand-in exposing exactly the h5py calls the loader makes -- `File(path, "r")`,
+    `.attrs[...]`, `in`, `group[name]`, `dataset[()]`, `.close()` -- whose `read()` is removed so that a call meant for the
+    built-in reader fails.  Same weights and the same optimiser state must come out of both branches."""
+    kh = pkg("keras_h5")
+    h5lite = pkg("h5lite")
+    closed = []
+
+    class _DS:
+        def __init__(self, d):
+            self._d, self.attrs, self.shape = d, d.attrs, d.shape
+
+        def __getitem__(self, key):
+            assert key == ()
+            return self._d.read()
+
+    class _Grp:
+        def __init__(self, g):
+            self._g, self.attrs = g, g.attrs
+
+        def __contains__(self, k):
+            return k in self._g
+
+        def __getitem__(self, k):
+            o = self._g[k]
+            return _Grp(o) if isinstance(o, h5lite.Group) else _DS(o)
+
+        def close(self):
+            closed.append(1)
+
+    class _FakeH5py:
+        @staticmethod
+        def File(path, mode="r"):
+            assert mode == "r"
+            return _Grp(h5lite.File(path))
+
+    ref_w = kh.load_dense_chain(trained_fixture["path"])
+    # a file with optimiser state, written by this repository's writer
+    tr = pkg("training")
+    opt = tr.Adam(0.003)
+    opt.iterations = 17
+    opt.m = np.linspace(-1, 1, ref_w.n_params()).astype(np.float32)
+    opt.v = np.linspace(0, 2, ref_w.n_params()).astype(np.float32)
+    path = str(tmp_path / "with_state.h5")
+    kh.save_dense_chain(path, ref_w, optimizer=opt)
+    ref_state = kh.load_optimizer_state(path)
+    monkeypatch.setattr(kh, "h5py", _FakeH5py)
+    monkeypatch.setattr(kh, "HAVE_H5PY", True)
+    w = kh.load_dense_chain(trained_fixture["path"])
+    assert w.layer_names == ref_w.layer_names and list(w.relu) == list(ref_w.relu) and w.name == ref_w.name
+    for a, b in zip(w.kernels + w.biases, ref_w.kernels + ref_w.biases):
+        assert np.array_equal(a, b)
+    st = kh.load_optimizer_state(path)
+    assert st.iterations == 17 == ref_state.iterations and st.learning_rate == ref_state.learning_rate
+    assert np.array_equal(st.m, ref_state.m) and np.array_equal(st.v, ref_state.v) and np.array_equal(st.m, opt.m)
+    assert len(closed) >= 3          # every h5py file the loader opened was closed again
+    with pytest.raises(IOError):
+        kh.load_dense_chain(str(tmp_path / "missing.h5"))
