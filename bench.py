@@ -129,6 +129,14 @@ def build_problem(rows, seed):
     return rm, ks, bs, relu, mu, sd, pmin, pmax, params
 
 
+def workload_config(rows, world):
+    """`config` of the JSON line: the WORKLOAD only, identical on both arms (the implementation that ran is named by the
+    top-level keys `impl`, `dtype` and `precision_path`)."""
+    return {"workload": "DirectEmulator.predict 7->288->352->288->224->451, full 451-bin output to HBM",
+            "rows_per_gpu": rows, "params_dtype": "f64", "weights": build_problem.weights,
+            "l2": "working set 1.86 GB/step >> 126 MB L2 (no flush needed)", "parallelism": f"rows sharded x{world}"}
+
+
 def make_cpu_port(rm, ks, bs, relu, mu, sd, pmin, pmax, threads, as_written_stats=None):
     """The oracle port on the host: float32 chain as full-batch SGEMMs (torch CPU, `threads` threads),
     fp64 parameter transform and fp32 de-normalisation in numpy.  `as_written_stats` =
@@ -215,8 +223,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "DirectEmulator.predict 7->288->352->288->224->451, full 451-bin output",
-                       "rows_per_gpu": rows, "params_dtype": "f64", "weights": build_problem.weights},
+            "config": workload_config(rows, max(1, args.gpus)), "precision_path": "fp32 (CPU port)",
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                              "as_written_batch32": b32},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -494,10 +501,8 @@ def main():
             "dtype": {"fp32": "f32", "bf16x3": "bf16x3 split, f32 accumulate", "fp16x3": "fp16x3 split, f32 accumulate",
                       "fp16e4m3": "fp16 + e4m3 first-order corrections, f32 accumulate"}[prec_name],
             "data": "synthetic",
-            "config": {"workload": "DirectEmulator.predict 7->288->352->288->224->451, full 451-bin output to HBM",
-                       "rows_per_gpu": n, "params_dtype": "f64", "precision_path": prec_name,
-                       "weights": build_problem.weights,
-                       "l2": "working set 1.86 GB/step >> 126 MB L2 (no flush needed)", "parallelism": f"rows sharded x{world}", "host_cores_bound": (len(numa_cores) if numa_cores else None)},
+            "config": workload_config(n, world), "precision_path": prec_name,
+            "host_cores_bound": (len(numa_cores) if numa_cores else None),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * 56, "d2h_bytes_per_step": n * 1804,
                     "steps": e2e_steps, "checksum": checksum, "seconds_per_step_by_rank": e2e_ranks,
                     "platform_ceiling": world * n / copy_s, "platform_ceiling_gbs": world * n * 1860 / copy_s / 1e9,

@@ -21,6 +21,13 @@ def test_reference_arm_prints_one_contract_line():
         assert key in d
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # `config` is the workload alone, built by the one function both arms call; what ran is named outside it
+    assert set(d["config"]) == {"workload", "rows_per_gpu", "params_dtype", "weights", "l2", "parallelism"}
+    assert d["config"]["rows_per_gpu"] == 4096 and "model" not in d["config"] and d["precision_path"].startswith("fp32")
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": workload_config(') == 2
+    b32 = d["cpu_baseline"]["as_written_batch32"]
+    assert b32["value"] > 0 and "32-row" in b32["sample"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():
