@@ -401,3 +401,31 @@ def test_the_h5py_branch_of_the_loader_on_an_h5py_shaped_file_object(monkeypatch
     assert len(closed) >= 3          # every h5py file the loader opened was closed again
     with pytest.raises(IOError):
         kh.load_dense_chain(str(tmp_path / "missing.h5"))
+
+
+def test_the_binding_stub_of_integration_md_binds_the_real_library(rm):
+    """INTEGRATION.md section B shows the file a maintainer of the reference would add.  Execute that very text against the built
+    library: every symbol it names must exist with the argument counts of include/vae21.h, and without a GPU its first call must
+    fail with the library's message, not crash."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = next(b for b in blocks if "VeryAccurateEmulator/_vae21.py" in b)
+    L = pkg("_lib")
+    stub = stub.replace('C.CDLL("libvae21.so")', f"C.CDLL({L.LIB_PATH!r})")
+    ns = {}
+    exec(compile(stub, "INTEGRATION.md:_vae21.py", "exec"), ns)
+    hdr = open(os.path.join(ROOT, "include", "vae21.h")).read()
+    for name in ("vae21_create", "vae21_set_model", "vae21_set_norm", "vae21_predict"):
+        proto = re.search(rf"\b{name}\s*\((.*?)\);", hdr, flags=re.S).group(1)
+        assert len(getattr(ns["_lib"], name).argtypes) == proto.count(",") + 1, name
+    ks, bs, relu = rm.glorot_chain((7, 16, 451), seed=1)
+    par = rm.draw_params(64, seed=2)
+    sig = np.random.default_rng(3).normal(size=(64, 451)).astype(np.float32)
+    if L.device_count() == 0:
+        with pytest.raises(RuntimeError, match="CUDA"):
+            ns["Handle"](ks, bs, [int(r) for r in relu], par, sig)
+    else:
+        h = ns["Handle"](ks, bs, [int(r) for r in relu], par, sig)
+        got = h.predict(par[:5])
+        want = rm.predict(par[:5], ks, bs, relu, *rm.par_stats(par), *rm.signal_stats(sig), squeeze=False)
+        assert np.max(np.abs(got - want) / np.max(np.abs(want), axis=1, keepdims=True)) < 1e-5
