@@ -429,3 +429,37 @@ def test_the_binding_stub_of_integration_md_binds_the_real_library(rm):
         got = h.predict(par[:5])
         want = rm.predict(par[:5], ks, bs, relu, *rm.par_stats(par), *rm.signal_stats(sig), squeeze=False)
         assert np.max(np.abs(got - want) / np.max(np.abs(want), axis=1, keepdims=True)) < 1e-5
+
+
+def test_the_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/vae21.h is the drop-in boundary: it must compile as strict C99 (and C++11), and a C program using it must link
+    against libvae21.so and get an error code -- not a crash -- from a call that cannot succeed."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    L = pkg("_lib")
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "vae21.h"\n'
+                   "int main(void) {\n"
+                   "  vae21_handle* h = 0;\n"
+                   "  if (vae21_version() != VAE21_VERSION) return 10;\n"
+                   "  if (vae21_predict(0, 0, VAE21_F64, 0, 0, 0, 0, VAE21_FP32_SIMT, 0) == 0) return 11;\n"
+                   "  if (vae21_last_error()[0] == 0) return 12;\n"
+                   "  if (vae21_create(-1, &h) == 0 || h != 0) return 13;\n"
+                   '  printf("%s\\n", vae21_last_error());\n'
+                   "  return 0;\n}\n")
+    inc = os.path.join(ROOT, "include")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)], check=True)
+    gxx = shutil.which("g++")
+    if gxx:
+        subprocess.run([gxx, "-std=c++11", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)], check=True)
+    exe = tmp_path / "t"
+    libdir = os.path.dirname(L.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-l:" + os.path.basename(L.LIB_PATH),
+                    "-Wl,-rpath," + libdir], check=True)
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, (p.returncode, p.stdout, p.stderr)
+    assert p.stdout.strip()
