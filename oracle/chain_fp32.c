@@ -9,6 +9,8 @@
  * oracle/refmath.py::dense_chain_fp32_ordered, whose "seq_fma" order emulates fmaf through float64 and is checked against this
  * file in tests/test_oracle.py).  A third implementation of the chain, sharing no code with the numpy and torch ones.
  *
+ * Measured on a B200: the FP32 CUDA kernel reproduces this function bit for bit (tests/test_zz_fp32_vs_c_oracle.py).
+ *
  * Parity status: as oracle/refmath.py -- pinned to float64 known answers from the reference's shipped weights; TensorFlow's own
  * output is unavailable (absent from the image), so bit-level parity with it is unpinned.
  *
