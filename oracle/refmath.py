@@ -18,7 +18,13 @@ Parity status: PARTIALLY PINNED.
     (models/autoencoder_based_emulator/{ae_emulator,decoder}.h5, SURVEY.md
     section 8c) -- see ``tests/golden/``.  No TF ``predict`` output vector
     exists anywhere in the reference, so bit-level parity with TF itself is
-    unpinned (DESIGN.md says so too).
+    unpinned (DESIGN.md says so too).  What that freedom is worth is
+    bounded: ``dense_chain_fp32_ordered`` evaluates the chain under eight
+    explicit float32 summation orders (all within 2e-6 of the amplitude of
+    the float64 arbiter, tests/test_oracle.py), its ``seq_fma`` order is
+    reproduced bit for bit by the plain-C chain ``oracle/chain_fp32.c``, and
+    the FP32 CUDA kernel reproduces that C chain bit for bit on a B200
+    (tests/test_zz_fp32_vs_c_oracle.py).
 
 Each function cites the reference lines it follows (paths relative to
 /root/reference).
